@@ -1,0 +1,324 @@
+"""Targets: the plugin surface of the hot path, GPU-backed.
+
+Mirrors the public interface of BayHunter's src/Targets.py (ObservedData :16-30,
+ModeledData :33-82, Valuation :85-183, SingleTarget :186-249, the six target
+classes :252-297, JointTarget :300-347) so that SingleChain.iterate() and
+MCMC_Optimizer can use these objects unchanged, but
+
+* `JointTarget.evaluate(h, vp, vs, noise)` runs forward models AND likelihood in
+  one call of the CUDA engine (batch of one), and
+* `JointTarget.evaluate_batch(...)` evaluates thousands of chains per launch.
+
+The covariance law of a target is whatever the chain bound to
+`target.get_covariance` (src/SingleChain.py:159-205); the bound method's name
+selects the device law.  The numpy bodies of `Valuation` exist because the chain
+binds and BayWatch/SynthObs call them; `evaluate` never uses them.
+"""
+import logging
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine, TargetSpec
+from .Models import pack_layers
+
+logger = logging.getLogger()
+
+RF_REFS = ("prf", "srf")
+SWD_REFS = ("rdispph", "ldispph", "rdispgr", "ldispgr")
+
+
+class ObservedData(object):
+    """x (monotone increasing), y = y(x), optional yerr (NaN vector if unusable)."""
+
+    def __init__(self, x, y, yerr=None):
+        self.x = x
+        self.y = y
+        self.yerr = yerr
+        if self.yerr is None or np.any(yerr <= 0.) or np.any(np.isnan(yerr)):
+            self.yerr = np.ones(x.size) * np.nan
+
+
+class ModeledData(object):
+    """Holds the forward-modelling plugin and the latest synthetic (x, y)."""
+
+    def __init__(self, obsx, ref):
+        if ref in RF_REFS:
+            from .rfmini_modrf import RFminiModRF
+            self.plugin = RFminiModRF(obsx, ref)
+            self.xlabel = "Time in s"
+        elif ref in SWD_REFS:
+            from .surf96_modsw import SurfDisp
+            self.plugin = SurfDisp(obsx, ref)
+            self.xlabel = "Period in s"
+        else:
+            logger.info("Please provide a forward modeling plugin for your target.\n"
+                        "Use target.update_plugin(MyForwardClass())")
+            self.plugin = None
+            self.xlabel = "x"
+        self.x = np.nan
+        self.y = np.nan
+
+    def update(self, plugin):
+        self.plugin = plugin
+
+    def calc_synth(self, h, vp, vs, **kwargs):
+        rho = kwargs.pop("rho")
+        self.x, self.y = self.plugin.run_model(h, vp, vs, rho=rho, **kwargs)
+
+
+class Valuation(object):
+    """Covariance-law constructors + log-likelihood (host utilities).
+
+    The chain binds one of the get_covariance_* methods per target; the device
+    likelihood is selected from that binding (see `covariance_law`)."""
+
+    def __init__(self):
+        self.corr_inv = None
+        self.logcorr_det = None
+        self.misfit = None
+        self.likelihood = None
+
+    @staticmethod
+    def get_rms(yobs, ymod):
+        return np.sqrt(np.mean((ymod - yobs) ** 2))
+
+    @staticmethod
+    def get_covariance_nocorr(sigma, size, yerr=None, corr=0):
+        return np.eye(size) / sigma ** 2, (2 * size) * np.log(sigma)
+
+    @staticmethod
+    def get_covariance_nocorr_scalederr(sigma, size, yerr, corr=0):
+        scaled_err = yerr / yerr.min()          # not squared: reference quirk (Targets.py:125-127)
+        return (np.eye(size) / (scaled_err * sigma ** 2),
+                (2 * size) * np.log(sigma) + np.log(np.prod(scaled_err)))
+
+    @staticmethod
+    def get_corr_inv(corr, size):
+        d = np.full(size, 1.0 + corr ** 2)
+        d[0] = d[-1] = 1
+        e = np.full(size - 1, -corr)
+        return np.diag(d) + np.diag(e, k=1) + np.diag(e, k=-1)
+
+    def get_covariance_exp(self, corr, sigma, size, yerr=None):
+        c_inv = self.get_corr_inv(corr, size) / (sigma ** 2 * (1 - corr ** 2))
+        return c_inv, (2 * size) * np.log(sigma) + (size - 1) * np.log(1 - corr ** 2)
+
+    def init_covariance_gauss(self, corr, size, rcond=None):
+        from .engine import gauss_corr_inverse
+        self.corr_inv, self.logcorr_det = gauss_corr_inverse(corr, size, rcond)
+
+    def get_covariance_gauss(self, sigma, size, yerr=None, corr=None):
+        return self.corr_inv / sigma ** 2, (2 * size) * np.log(sigma) + self.logcorr_det
+
+    @staticmethod
+    def get_likelihood(yobs, ymod, c_inv, logc_det):
+        ydiff = ymod - yobs
+        madist = ydiff.dot(c_inv).dot(ydiff)
+        return -0.5 * (yobs.size * np.log(2 * np.pi) + logc_det) - madist / 2.
+
+
+_LAW_BY_METHOD = {"get_covariance_exp": "exp", "get_covariance_nocorr": "white",
+                  "get_covariance_nocorr_scalederr": "white_scaled", "get_covariance_gauss": "gauss"}
+
+
+class SingleTarget(object):
+    """Observed + modelled data + valuation of one data set."""
+
+    def __init__(self, x, y, ref, yerr=None):
+        self.ref = ref
+        self.obsdata = ObservedData(x=x, y=y, yerr=yerr)
+        self.moddata = ModeledData(obsx=x, ref=ref)
+        self.valuation = Valuation()
+        self.get_covariance = None     # bound by the chain (SingleChain.py:175-205)
+        logger.info("Initiated target: %s (ref: %s)" % (self.__class__.__name__, self.ref))
+
+    def update_plugin(self, plugin):
+        self.moddata.update(plugin)
+
+    def covariance_law(self):
+        """Name of the device law matching the bound get_covariance method."""
+        name = getattr(self.get_covariance, "__name__", None)
+        if name is None:
+            return "exp"    # unbound: the law BayHunter uses for a free correlation
+        try:
+            return _LAW_BY_METHOD[name]
+        except KeyError:
+            raise ValueError("target %s: get_covariance is bound to %r, which has no device "
+                             "equivalent" % (self.ref, name))
+
+    def _moddata_valid(self):
+        if not type(self.moddata.x) == np.ndarray:
+            return False
+        if not len(self.obsdata.x) == len(self.moddata.x):
+            return False
+        if not np.sum(self.obsdata.x - self.moddata.x) <= 1e-5:
+            return False
+        if not len(self.obsdata.y) == len(self.moddata.y):
+            return False
+        return True
+
+    def calc_misfit(self):
+        if not self._moddata_valid():
+            self.valuation.misfit = 1e15
+            return
+        self.valuation.misfit = self.valuation.get_rms(self.obsdata.y, self.moddata.y)
+
+    def calc_likelihood(self, c_inv, logc_det):
+        if not self._moddata_valid():
+            self.valuation.likelihood = -1e15
+            return
+        self.valuation.likelihood = self.valuation.get_likelihood(
+            self.obsdata.y, self.moddata.y, c_inv, logc_det)
+
+    def to_spec(self):
+        """Engine description of this target (observed data, law, plugin parameters)."""
+        law = self.covariance_law()
+        plugin = self.moddata.plugin
+        params = dict(getattr(plugin, "modelparams", {}))
+        params.pop("water", None)
+        wtype = params.pop("wtype", None)
+        if wtype is not None and {"P": "prf", "SV": "srf"}.get(wtype) != self.ref:
+            raise ValueError("target %s: wtype %r contradicts the target reference" % (self.ref, wtype))
+        kw = {}
+        if law == "white_scaled":
+            kw["yerr"] = self.obsdata.yerr
+        if law == "gauss":
+            kw["corr_inv"] = self.valuation.corr_inv
+            kw["logcorr_det"] = self.valuation.logcorr_det
+        y = self.obsdata.y if self.obsdata.y is not None else np.zeros(self.obsdata.x.size)
+        return TargetSpec(self.ref, self.obsdata.x, y, cov=law, **kw, **params)
+
+
+class RayleighDispersionPhase(SingleTarget):
+    noiseref = "swd"
+
+    def __init__(self, x, y, yerr=None):
+        SingleTarget.__init__(self, x, y, "rdispph", yerr=yerr)
+
+
+class RayleighDispersionGroup(SingleTarget):
+    noiseref = "swd"
+
+    def __init__(self, x, y, yerr=None):
+        SingleTarget.__init__(self, x, y, "rdispgr", yerr=yerr)
+
+
+class LoveDispersionPhase(SingleTarget):
+    noiseref = "swd"
+
+    def __init__(self, x, y, yerr=None):
+        SingleTarget.__init__(self, x, y, "ldispph", yerr=yerr)
+
+
+class LoveDispersionGroup(SingleTarget):
+    noiseref = "swd"
+
+    def __init__(self, x, y, yerr=None):
+        SingleTarget.__init__(self, x, y, "ldispgr", yerr=yerr)
+
+
+class PReceiverFunction(SingleTarget):
+    noiseref = "rf"
+
+    def __init__(self, x, y, yerr=None):
+        SingleTarget.__init__(self, x, y, "prf", yerr=yerr)
+
+
+class SReceiverFunction(SingleTarget):
+    noiseref = "rf"
+
+    def __init__(self, x, y, yerr=None):
+        SingleTarget.__init__(self, x, y, "srf", yerr=yerr)
+
+
+class JointTarget(object):
+    """List of SingleTargets; joint log-likelihood of a model (or of a batch)."""
+
+    def __init__(self, targets):
+        self.targets = targets
+        self.ntargets = len(targets)
+        self._engine = None
+        self._engine_key = None
+
+    # pickling: engines hold device handles -> dropped, rebuilt lazily
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        d["_engine_key"] = None
+        return d
+
+    def get_misfits(self):
+        misfits = [target.valuation.misfit for target in self.targets]
+        return np.concatenate((misfits, [np.sum(misfits)]))
+
+    def _all_native(self):
+        from .rfmini_modrf import RFminiModRF
+        from .surf96_modsw import SurfDisp
+        return all(isinstance(t.moddata.plugin, (RFminiModRF, SurfDisp)) for t in self.targets)
+
+    def engine(self, max_batch=1, max_layers=_lib.MAX_LAYERS):
+        """Engine bound to the current laws/parameters (rebuilt when they change)."""
+        specs = [t.to_spec() for t in self.targets]
+        key = (tuple((s.ref, s.cov, s.n, tuple(sorted((k, str(v)) for k, v in s.params.items())),
+                      s.y.tobytes()) for s in specs), max_batch, max_layers)
+        if self._engine is None or self._engine_key[0] != key[0] or \
+                self._engine.max_batch < max_batch or self._engine.max_layers < max_layers:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(specs, max_batch, max_layers)
+            self._engine_key = key
+        return self._engine
+
+    def evaluate(self, h, vp, vs, noise, **kwargs):
+        """Single-model evaluation with BayHunter's semantics (src/Targets.py:314-347):
+        leaves `proposallikelihood` (float) and `proposalmisfits` (length T+1)."""
+        if not self._all_native():
+            return self._evaluate_foreign_plugins(h, vp, vs, noise, **kwargs)
+        if any(k in kwargs for k in ("qp", "qs")):
+            raise NotImplementedError("per-layer qp/qs arrays are only supported through "
+                                      "plugin.run_model, not through the fused evaluate")
+        h = np.asarray(h, dtype=np.float64)
+        rows = pack_layers(h, vp, vs)[None]
+        nlay = np.array([h.size], dtype=np.int32)
+        rho = kwargs.pop("rho", None)
+        if rho is not None:
+            rho = np.ascontiguousarray(rho, dtype=np.float64)[None]
+        eng = self.engine(1, max(h.size, 2))
+        logL, misfits, status, synth = eng.eval_host(
+            rows, nlay, np.asarray(noise, dtype=np.float64)[None], rho=rho, want_synth=True)
+        for target, ys in zip(self.targets, eng.split_synth(synth[0])):
+            if status[0]:
+                target.moddata.x, target.moddata.y = target.obsdata.x, ys.copy()
+            else:
+                target.moddata.x, target.moddata.y = np.nan, np.nan
+        if not status[0]:
+            self.proposallikelihood = -1e15
+            self.proposalmisfits = [1e15] * (self.ntargets + 1)
+            return
+        for target, m in zip(self.targets, misfits[0]):
+            target.valuation.misfit = m
+        self.proposallikelihood = float(logL[0])
+        self.proposalmisfits = misfits[0].copy()
+
+    def _evaluate_foreign_plugins(self, h, vp, vs, noise, **kwargs):
+        """A user plugin (templates/myfwd.py contract) is attached to at least one
+        target.  Its forward model is host code this engine cannot run on the
+        device, and this package deliberately has no host likelihood path."""
+        raise NotImplementedError(
+            "JointTarget.evaluate: a non-native forward plugin is attached; bayhunter_b200 only "
+            "evaluates its own SurfDisp / RFminiModRF targets (no CPU likelihood path). Inject "
+            "bayhunter_b200 plugins into the reference's own Targets objects instead.")
+
+    def evaluate_batch(self, rows, nlay, noise, rho=None, want_synth=False):
+        """Batched evaluation.  Accepts torch CUDA tensors (device path) or numpy
+        arrays / CPU tensors (host path: copies happen inside the C call).
+        rows [B,L,4] = (vs, vp/vs, z_top, h); nlay [B]; noise [B,2T].
+        Returns (logL [B], misfits [B,T+1], status [B], synth | None)."""
+        B, L = int(rows.shape[0]), int(rows.shape[1])
+        eng = self.engine(B, L)
+        if hasattr(rows, "is_cuda") and rows.is_cuda:
+            return eng.eval(rows, nlay, noise, rho=rho, want_synth=want_synth)
+        to_np = lambda a: a.numpy() if hasattr(a, "numpy") else a
+        return eng.eval_host(to_np(rows), to_np(nlay), to_np(noise),
+                             rho=None if rho is None else to_np(rho), want_synth=want_synth)

@@ -1,0 +1,108 @@
+"""ctypes binding of libbayhunter_b200.so (C ABI in include/bayhunter_b200.h).
+
+The library is the product: if it cannot be loaded (or built), importing the
+compute entry points raises -- there is no Python/NumPy fallback for the hot path.
+"""
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+BH_OK = 0
+BH_ERR_ARG, BH_ERR_CUDA, BH_ERR_UNSUPPORTED, BH_ERR_NO_DEVICE = -1, -2, -3, -4
+
+REF_CODES = {"rdispph": 0, "rdispgr": 1, "ldispph": 2, "ldispgr": 3, "prf": 4, "srf": 5}
+COV_EXP, COV_WHITE, COV_WHITE_SCALED, COV_GAUSS = 0, 1, 2, 3
+MAX_TARGETS, MAX_PERIODS, MAX_LAYERS = 8, 60, 100
+KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik")
+
+
+class BhTarget(ctypes.Structure):
+    """struct bh_target (include/bayhunter_b200.h)."""
+    _fields_ = [
+        ("ref", ctypes.c_int), ("n", ctypes.c_int),
+        ("x", c_double_p), ("y", c_double_p), ("yerr", c_double_p),
+        ("cov", ctypes.c_int), ("corr_inv", c_double_p), ("logcorr_det", ctypes.c_double),
+        ("mode", ctypes.c_int), ("flsph", ctypes.c_int),
+        ("gauss", ctypes.c_double), ("p", ctypes.c_double), ("nsv", ctypes.c_double),
+        ("qp", ctypes.c_double), ("qs", ctypes.c_double),
+    ]
+
+
+class BayHunterB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libbayhunter_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+# every symbol include/bayhunter_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "bh_abi_version": (ctypes.c_int, []),
+    "bh_last_error": (ctypes.c_char_p, []),
+    "bh_device_count": (ctypes.c_int, []),
+    "bh_engine_create": (ctypes.c_int, [ctypes.POINTER(BhTarget), ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bh_engine_destroy": (None, [ctypes.c_void_p]),
+    "bh_engine_synth_stride": (ctypes.c_int, [ctypes.c_void_p]),
+    "bh_engine_set": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    "bh_engine_eval": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 4 +
+                       [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5),
+    "bh_engine_eval_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 4 +
+                            [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "bh_engine_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "bh_engine_last_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
+    "bh_surfdisp96": (ctypes.c_int, [c_float_p] * 4 + [ctypes.c_int] * 6 +
+                      [c_double_p, c_double_p, c_int_p]),
+    "bh_synrf": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 +
+                 [c_double_p] * 9),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if the shared object is missing) and type the ABI."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise BayHunterB200Error(BH_ERR_NO_DEVICE, "%s is missing; run __graft_entry__.build()" % path)
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.bh_abi_version() != 1:
+            raise BayHunterB200Error(BH_ERR_ARG, "ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(code):
+    if code != BH_OK:
+        msg = load().bh_last_error()
+        raise BayHunterB200Error(code, msg.decode() if msg else "")
+    return code
+
+
+def require_device():
+    """Fail loudly when no CUDA device is usable -- the hot path has no CPU route."""
+    lib = load()
+    if lib.bh_device_count() < 1:
+        raise BayHunterB200Error(BH_ERR_NO_DEVICE,
+                                 "no CUDA device visible; bayhunter_b200 has no CPU path")
+    return lib

@@ -1,0 +1,62 @@
+"""Build libbayhunter_b200.so (hand-written sm_100a CUDA + the C ABI) in-tree.
+
+nvcc cross-compiles without a GPU; the resulting shared object travels with
+the repository snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbayhunter_b200.so")
+SOURCES = ["engine.cu", "prep_kernel.cu", "swd_kernel.cu", "rf_kernel.cu", "loglik_kernel.cu"]
+HEADERS = ["bh_common.cuh", "swd_core.cuh", "rf_core.cuh", "kernels.h",
+           os.path.join("..", "..", "include", "bayhunter_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "-shared",
+    "-cudart", "static",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libbayhunter_b200.so")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False, extra=()):
+    """Compile every CUDA source for sm_100a into one shared library."""
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libbayhunter_b200.so")
+    if verbose and (res.stdout or res.stderr):
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True,
+          extra=("-Xptxas", "-v") if "--ptxas" in sys.argv else ())
+    print(LIB)

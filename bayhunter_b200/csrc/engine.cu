@@ -1,0 +1,544 @@
+// engine.cu -- C ABI of libbayhunter_b200.so (see include/bayhunter_b200.h).
+//
+// Owns the device-resident constants of a joint target set, the per-batch
+// scratch, and the launch schedule of one joint evaluation:
+//
+//   stream S  : prepare(SWD rows) -> swd_kernel ----------------------+
+//   stream A  : prepare(RF tables) -> rf_spectrum -> rf_synth --(join)-+-> loglik
+//
+// The SWD kernel is latency bound (few, long, serial searches); the RF spectrum
+// kernel is throughput bound ((model, frequency) items by the million).  Forking
+// them onto two streams lets the RF warps fill the issue slots the SWD warps
+// leave idle.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bayhunter_b200.h"
+#include "kernels.h"
+
+using namespace bh;
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const char* what, cudaError_t ce = cudaSuccess) {
+  g_err = what;
+  if (ce != cudaSuccess) {
+    g_err += ": ";
+    g_err += cudaGetErrorString(ce);
+  }
+  return code;
+}
+
+#define BH_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (call);                                                 \
+    if (_e != cudaSuccess) return set_err(BH_ERR_CUDA, #call, _e);           \
+  } while (0)
+
+template <class T>
+int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) return BH_OK;
+  BH_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  return BH_OK;
+}
+
+int odd_stride(int lmax) { return (lmax & 1) ? lmax : lmax + 1; }
+
+bool is_swd(int ref) { return ref >= BH_REF_RDISPPH && ref <= BH_REF_LDISPGR; }
+bool is_rf(int ref) { return ref == BH_REF_PRF || ref == BH_REF_SRF; }
+
+}  // namespace
+
+struct bh_engine {
+  TargetSet ts{};
+  int max_batch = 0, max_layers = 0;
+  std::vector<void*> owned;   // device allocations freed on destroy
+  // scratch
+  PrepOut prep{};
+  cd* spec = nullptr;
+  double* curves = nullptr;
+  int curve_stride = 0;
+  int curve_off[kMaxTargets] = {0};
+  double* rfsynth = nullptr;
+  int* tstatus = nullptr;
+  unsigned long long* counters = nullptr;
+  int max_nfreq = 0;
+  // device mirrors for the host-pointer entry point
+  double *d_model = nullptr, *d_noise = nullptr, *d_rho = nullptr, *d_logL = nullptr,
+         *d_misfits = nullptr, *d_synth = nullptr;
+  int *d_nlay = nullptr, *d_status = nullptr;
+  cudaStream_t s_own = nullptr, s_aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // tunables
+  int searches_per_warp = 0;  // 0 = auto
+  int max_spec = 8;
+  int concurrent = 1;
+  // optional per-kernel timing (bh_engine_set "profile"): event pairs around
+  // each launch, recorded on the stream the kernel is launched on
+  int profile = 0;
+  cudaEvent_t pev[2 * BH_NUM_KERNELS] = {nullptr};
+  bool pev_used[BH_NUM_KERNELS] = {false};
+};
+
+namespace {
+struct KTimer {   // records start in ctor, stop in dtor when profiling is on
+  bh_engine* e; int k; cudaStream_t st;
+  KTimer(bh_engine* e_, int k_, cudaStream_t st_) : e(e_), k(k_), st(st_) {
+    if (e->profile) { cudaEventRecord(e->pev[2 * k], st); e->pev_used[k] = true; }
+  }
+  ~KTimer() { if (e->profile) cudaEventRecord(e->pev[2 * k + 1], st); }
+};
+}  // namespace
+
+static int upload(bh_engine* e, const double* host, size_t n, const double** dev) {
+  double* d = nullptr;
+  int rc = dev_alloc(&d, n);
+  if (rc != BH_OK) return rc;
+  e->owned.push_back(d);
+  BH_CUDA(cudaMemcpy(d, host, n * sizeof(double), cudaMemcpyHostToDevice));
+  *dev = d;
+  return BH_OK;
+}
+
+template <class T>
+static int scratch(bh_engine* e, T** p, size_t n) {
+  int rc = dev_alloc(p, n);
+  if (rc == BH_OK && *p) e->owned.push_back(*p);
+  return rc;
+}
+
+extern "C" {
+
+int bh_abi_version(void) { return BH_ABI_VERSION; }
+
+const char* bh_last_error(void) { return g_err.c_str(); }
+
+int bh_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void bh_engine_destroy(bh_engine* e) {
+  if (!e) return;
+  for (void* p : e->owned) cudaFree(p);
+  for (cudaEvent_t ev : e->pev) if (ev) cudaEventDestroy(ev);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->s_own) cudaStreamDestroy(e->s_own);
+  if (e->s_aux) cudaStreamDestroy(e->s_aux);
+  delete e;
+}
+
+int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int max_layers,
+                     bh_engine** out) {
+  if (!out) return set_err(BH_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!targets || ntargets < 1 || ntargets > BH_MAX_TARGETS)
+    return set_err(BH_ERR_ARG, "ntargets must be 1..BH_MAX_TARGETS");
+  if (max_batch < 1 || max_layers < 1 || max_layers > BH_MAX_LAYERS)
+    return set_err(BH_ERR_ARG, "max_batch >= 1 and 1 <= max_layers <= 100 required");
+  if (bh_device_count() < 1)
+    return set_err(BH_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+
+  bh_engine* e = new bh_engine();
+  e->max_batch = max_batch;
+  e->max_layers = max_layers;
+  e->ts.ntargets = ntargets;
+  int off = 0, coff = 0, nrf = 0;
+  int rc = BH_OK;
+  for (int t = 0; t < ntargets && rc == BH_OK; ++t) {
+    const bh_target& s = targets[t];
+    TargetDev& d = e->ts.t[t];
+    memset(&d, 0, sizeof(d));
+    if (s.n < 1 || !s.x || !s.y) { rc = set_err(BH_ERR_ARG, "target needs n >= 1, x and y"); break; }
+    if (!is_swd(s.ref) && !is_rf(s.ref)) { rc = set_err(BH_ERR_ARG, "unknown target ref"); break; }
+    d.ref = s.ref; d.n = s.n; d.cov = s.cov; d.synth_off = off;
+    off += s.n;
+    if ((rc = upload(e, s.x, s.n, &d.x)) != BH_OK) break;
+    if ((rc = upload(e, s.y, s.n, &d.y)) != BH_OK) break;
+    if (s.cov == BH_COV_WHITE_SCALED) {
+      if (!s.yerr) { rc = set_err(BH_ERR_ARG, "BH_COV_WHITE_SCALED needs yerr"); break; }
+      // scaled_err = yerr / yerr.min(); log(prod(scaled_err))  (Targets.py:125-128)
+      std::vector<double> se(s.n);
+      double mn = s.yerr[0];
+      for (int i = 1; i < s.n; ++i) if (s.yerr[i] < mn) mn = s.yerr[i];
+      double prod = 1.0;
+      for (int i = 0; i < s.n; ++i) { se[i] = s.yerr[i] / mn; prod *= se[i]; }
+      d.log_serr_prod = log(prod);
+      if ((rc = upload(e, se.data(), s.n, &d.serr)) != BH_OK) break;
+    } else if (s.cov == BH_COV_GAUSS) {
+      if (!s.corr_inv) { rc = set_err(BH_ERR_ARG, "BH_COV_GAUSS needs corr_inv"); break; }
+      if ((rc = upload(e, s.corr_inv, (size_t)s.n * s.n, &d.corr_inv)) != BH_OK) break;
+      d.logcorr_det = s.logcorr_det;
+    } else if (s.cov != BH_COV_EXP && s.cov != BH_COV_WHITE) {
+      rc = set_err(BH_ERR_ARG, "unknown covariance law"); break;
+    }
+    e->curve_off[t] = coff;
+    if (is_swd(s.ref)) {
+      if (s.mode != 1) { rc = set_err(BH_ERR_UNSUPPORTED, "only mode = 1 (fundamental) is implemented"); break; }
+      if (s.flsph != 0) { rc = set_err(BH_ERR_UNSUPPORTED, "only flsph = 0 (flat earth) is implemented"); break; }
+      d.wave = (s.ref == BH_REF_RDISPPH || s.ref == BH_REF_RDISPGR) ? 2 : 1;   // surf96_modsw.py:48-59
+      d.igr = (s.ref == BH_REF_RDISPGR || s.ref == BH_REF_LDISPGR) ? 1 : 0;
+      if (s.n > BH_MAX_PERIODS) {
+        // surf96_modsw.py:35-43: 60-point linspace over [min, max], np.interp back
+        double mn = s.x[0], mx = s.x[0];
+        for (int i = 1; i < s.n; ++i) { if (s.x[i] < mn) mn = s.x[i]; if (s.x[i] > mx) mx = s.x[i]; }
+        std::vector<double> pi(BH_MAX_PERIODS);
+        const double step = (mx - mn) / (BH_MAX_PERIODS - 1);
+        for (int i = 0; i < BH_MAX_PERIODS; ++i) pi[i] = mn + i * step;   // numpy.linspace
+        pi[BH_MAX_PERIODS - 1] = mx;
+        d.kmax = BH_MAX_PERIODS;
+        if ((rc = upload(e, pi.data(), BH_MAX_PERIODS, &d.periods)) != BH_OK) break;
+      } else {
+        d.kmax = s.n;
+        d.periods = d.x;
+      }
+      coff += d.kmax;
+    } else {
+      // rfmini_modrf.py:41-62: fsamp, tshft, nsamp from the observed time axis
+      if (s.n < 2) { rc = set_err(BH_ERR_ARG, "RF target needs >= 2 samples"); break; }
+      double dt = round((s.x[1] - s.x[0]) * 1e4) / 1e4;
+      for (int i = 2; i < s.n; ++i) {
+        double di = round((s.x[i] - s.x[i - 1]) * 1e4) / 1e4;
+        if (di != dt) { rc = set_err(BH_ERR_ARG, "RF sampling rate must be constant"); break; }
+      }
+      if (rc != BH_OK) break;
+      d.fsamp = 1.0 / dt;
+      d.tshift = -s.x[0];
+      int ns = 1;
+      while (ns < 2 * s.n) ns <<= 1;        // 2**ceil(log2(2*ndata))
+      d.nsamp = ns;
+      d.waveno = (s.ref == BH_REF_SRF) ? 1 : 0;
+      d.gauss = s.gauss; d.p = s.p; d.nsv = s.nsv;
+      d.qp = s.qp > 0 ? s.qp : 500.0;      // rfmini_modrf.py:119-120
+      d.qs = s.qs > 0 ? s.qs : 225.0;
+      if (ns / 2 + 1 > e->max_nfreq) e->max_nfreq = ns / 2 + 1;
+      ++nrf;
+    }
+  }
+  e->ts.synth_stride = off;
+  e->curve_stride = coff > 0 ? coff : 1;
+  const size_t B = (size_t)max_batch, L = (size_t)max_layers;
+  e->prep.swd_stride = odd_stride(max_layers);
+  if (rc == BH_OK) rc = scratch(e, &e->prep.swd_rows, B * e->prep.swd_stride);
+  if (rc == BH_OK && nrf) rc = scratch(e, &e->prep.rf_lay, B * L);
+  if (rc == BH_OK && nrf) rc = scratch(e, &e->prep.rf_coef, B * L * 4);
+  if (rc == BH_OK && nrf) rc = scratch(e, &e->prep.rf_mc, B * 16);
+  if (rc == BH_OK && nrf) rc = scratch(e, &e->spec, B * e->max_nfreq);
+  if (rc == BH_OK) rc = scratch(e, &e->curves, B * e->curve_stride);
+  if (rc == BH_OK) rc = scratch(e, &e->rfsynth, B * (size_t)off);
+  if (rc == BH_OK) rc = scratch(e, &e->tstatus, B * kMaxTargets);
+  if (rc == BH_OK) rc = scratch(e, &e->counters, 2);
+  if (rc == BH_OK) rc = scratch(e, &e->d_model, B * L * 4);
+  if (rc == BH_OK) rc = scratch(e, &e->d_nlay, B);
+  if (rc == BH_OK) rc = scratch(e, &e->d_noise, B * 2 * ntargets);
+  if (rc == BH_OK) rc = scratch(e, &e->d_rho, B * L);
+  if (rc == BH_OK) rc = scratch(e, &e->d_logL, B);
+  if (rc == BH_OK) rc = scratch(e, &e->d_misfits, B * (ntargets + 1));
+  if (rc == BH_OK) rc = scratch(e, &e->d_status, B);
+  if (rc == BH_OK) rc = scratch(e, &e->d_synth, B * (size_t)off);
+  if (rc == BH_OK) {
+    cudaError_t ce;
+    if ((ce = cudaStreamCreateWithFlags(&e->s_own, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming)) != cudaSuccess)
+      rc = set_err(BH_ERR_CUDA, "stream/event creation", ce);
+  }
+  if (rc == BH_OK && cudaMemset(e->counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
+    rc = set_err(BH_ERR_CUDA, "cudaMemset(counters)");
+  if (rc != BH_OK) { std::string keep = g_err; bh_engine_destroy(e); g_err = keep; return rc; }
+  *out = e;
+  return BH_OK;
+}
+
+int bh_engine_synth_stride(const bh_engine* e) { return e ? e->ts.synth_stride : BH_ERR_ARG; }
+
+int bh_engine_set(bh_engine* e, const char* key, int value) {
+  if (!e || !key) return set_err(BH_ERR_ARG, "null engine/key");
+  if (!strcmp(key, "swd_searches_per_warp")) {
+    if (value < 0 || value > 32 || (value & (value - 1))) return set_err(BH_ERR_ARG, "searches_per_warp must be 0 (auto) or a power of two <= 32");
+    e->searches_per_warp = value;
+  } else if (!strcmp(key, "swd_max_spec")) {
+    if (value < 1 || value > 32) return set_err(BH_ERR_ARG, "swd_max_spec must be 1..32");
+    e->max_spec = value;
+  } else if (!strcmp(key, "concurrent")) {
+    e->concurrent = value ? 1 : 0;
+  } else if (!strcmp(key, "profile")) {
+    e->profile = value ? 1 : 0;
+    if (e->profile && !e->pev[0])
+      for (int i = 0; i < 2 * BH_NUM_KERNELS; ++i) BH_CUDA(cudaEventCreate(&e->pev[i]));
+  } else {
+    return set_err(BH_ERR_ARG, "unknown tunable");
+  }
+  return BH_OK;
+}
+
+int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const double* noise,
+                   const double* rho, int B, int lmax, double* logL, double* misfits, int* status,
+                   double* synth, void* stream) {
+  if (!e || !model || !nlay || !noise || !logL || !misfits || !status)
+    return set_err(BH_ERR_ARG, "null argument");
+  if (B < 0 || B > e->max_batch) return set_err(BH_ERR_ARG, "B exceeds max_batch");
+  if (lmax < 1 || lmax > e->max_layers) return set_err(BH_ERR_ARG, "lmax exceeds max_layers");
+  if (B == 0) return BH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const TargetSet& ts = e->ts;
+
+  SwdLaunch sw{};
+  int first_rf = -1;
+  for (int t = 0; t < ts.ntargets; ++t) {
+    const TargetDev& d = ts.t[t];
+    if (is_swd(d.ref)) {
+      int c = sw.ncurves++;
+      sw.target_id[c] = t; sw.wave[c] = d.wave; sw.igr[c] = d.igr; sw.kmax[c] = d.kmax;
+      sw.periods[c] = d.periods; sw.curve_off[c] = e->curve_off[t]; sw.synth_off[c] = d.synth_off;
+    } else if (first_rf < 0) {
+      first_rf = t;
+    }
+  }
+  const bool have_rf = first_rf >= 0;
+  PrepOut prep = e->prep;
+  prep.swd_stride = odd_stride(lmax);   // rows of this batch; buffer is sized for max_layers
+  BH_CUDA(cudaMemsetAsync(e->counters, 0, 2 * sizeof(unsigned long long), st));
+
+  cudaStream_t st_rf = st;
+  if (have_rf && sw.ncurves > 0 && e->concurrent) {
+    BH_CUDA(cudaEventRecord(e->ev_fork, st));
+    BH_CUDA(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
+    st_rf = e->s_aux;
+  }
+
+  for (bool& u : e->pev_used) u = false;
+  if (sw.ncurves > 0) {
+    { KTimer kt(e, BH_K_PREP_SWD, st);
+      launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st); }
+    sw.rows = prep.swd_rows; sw.row_stride = prep.swd_stride; sw.nlay = nlay; sw.B = B;
+    sw.curves = e->curves; sw.curve_stride = e->curve_stride;
+    sw.tstatus = e->tstatus; sw.counters = e->counters;
+    int S = e->searches_per_warp;
+    if (S == 0) {
+      // enough warps to give every SM sub-partition a few (148 SMs x 4 x ~3.5)
+      const long long nsearch = (long long)B * sw.ncurves;
+      S = 32;
+      while (S > 1 && nsearch / S < 2048) S >>= 1;
+    }
+    sw.searches_per_warp = S;
+    sw.max_spec = e->max_spec;
+    { KTimer kt(e, BH_K_SWD, st); launch_swd(sw, st); }
+  }
+  for (int t = 0; t < ts.ntargets; ++t) {
+    const TargetDev& d = ts.t[t];
+    if (!is_rf(d.ref)) continue;
+    { KTimer kt(e, BH_K_PREP_RF, st_rf);
+      launch_prepare(model, nlay, rho, B, lmax, false, true, d.p, d.nsv, d.qp, d.qs, prep, st_rf); }
+    RfLaunch rf{};
+    rf.lay = prep.rf_lay; rf.coef = prep.rf_coef; rf.mc = prep.rf_mc; rf.nlay = nlay;
+    rf.B = B; rf.lmax = lmax;
+    rf.k.dw = 2.0 * RF_PI * d.fsamp / d.nsamp;
+    rf.k.wref = 2.0 * RF_PI * 1.0;
+    rf.k.a = d.gauss; rf.k.tshift = d.tshift;
+    rf.k.qn = sqrt(RF_PI) * d.fsamp / d.gauss;
+    rf.k.u = d.p * RF_DEG_PER_KM;
+    rf.k.waveno = d.waveno; rf.k.nsamp = d.nsamp;
+    rf.spec = e->spec;
+    rf.out = e->rfsynth; rf.out_stride = ts.synth_stride; rf.out_off = d.synth_off; rf.ndata = d.n;
+    rf.tstatus = e->tstatus; rf.target_id = t;
+    { KTimer kt(e, BH_K_RF_SPECTRUM, st_rf); launch_rf_spectrum(rf, st_rf); }
+    { KTimer kt(e, BH_K_RF_SYNTH, st_rf); launch_rf_synth(rf, st_rf); }
+  }
+  if (st_rf != st) {
+    BH_CUDA(cudaEventRecord(e->ev_join, st_rf));
+    BH_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+  }
+  LoglikLaunch ll{};
+  ll.ts = ts;
+  ll.curves = e->curves; ll.curve_stride = e->curve_stride;
+  for (int t = 0; t < ts.ntargets; ++t) ll.curve_off[t] = e->curve_off[t];
+  ll.rfsynth = e->rfsynth; ll.tstatus = e->tstatus; ll.noise = noise; ll.B = B;
+  ll.logL = logL; ll.misfits = misfits; ll.status = status; ll.synth = synth;
+  { KTimer kt(e, BH_K_LOGLIK, st); launch_loglik(ll, st); }
+  BH_CUDA(cudaGetLastError());
+  return BH_OK;
+}
+
+int bh_engine_last_kernel_ms(bh_engine* e, float* ms) {
+  if (!e || !ms) return set_err(BH_ERR_ARG, "null argument");
+  if (!e->profile) return set_err(BH_ERR_ARG, "profiling is off: bh_engine_set(e, \"profile\", 1)");
+  for (int k = 0; k < BH_NUM_KERNELS; ++k) {
+    ms[k] = -1.0f;
+    if (!e->pev_used[k]) continue;
+    BH_CUDA(cudaEventSynchronize(e->pev[2 * k + 1]));
+    BH_CUDA(cudaEventElapsedTime(&ms[k], e->pev[2 * k], e->pev[2 * k + 1]));
+  }
+  return BH_OK;
+}
+
+int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay, const double* noise,
+                        const double* rho, int B, int lmax, double* logL, double* misfits,
+                        int* status, double* synth) {
+  if (!e || !model || !nlay || !noise || !logL || !misfits || !status)
+    return set_err(BH_ERR_ARG, "null argument");
+  if (B < 0 || B > e->max_batch) return set_err(BH_ERR_ARG, "B exceeds max_batch");
+  if (lmax < 1 || lmax > e->max_layers) return set_err(BH_ERR_ARG, "lmax exceeds max_layers");
+  if (B == 0) return BH_OK;
+  const int T = e->ts.ntargets;
+  cudaStream_t st = e->s_own;
+  const size_t nb = (size_t)B;
+  BH_CUDA(cudaMemcpyAsync(e->d_model, model, nb * lmax * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  BH_CUDA(cudaMemcpyAsync(e->d_nlay, nlay, nb * sizeof(int), cudaMemcpyHostToDevice, st));
+  BH_CUDA(cudaMemcpyAsync(e->d_noise, noise, nb * 2 * T * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (rho) BH_CUDA(cudaMemcpyAsync(e->d_rho, rho, nb * lmax * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = bh_engine_eval(e, e->d_model, e->d_nlay, e->d_noise, rho ? e->d_rho : nullptr, B, lmax,
+                          e->d_logL, e->d_misfits, e->d_status, synth ? e->d_synth : nullptr, st);
+  if (rc != BH_OK) return rc;
+  BH_CUDA(cudaMemcpyAsync(logL, e->d_logL, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BH_CUDA(cudaMemcpyAsync(misfits, e->d_misfits, nb * (T + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BH_CUDA(cudaMemcpyAsync(status, e->d_status, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (synth)
+    BH_CUDA(cudaMemcpyAsync(synth, e->d_synth, nb * e->ts.synth_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BH_CUDA(cudaStreamSynchronize(st));
+  return BH_OK;
+}
+
+int bh_engine_last_counts(bh_engine* e, long long* nsec) {
+  if (!e || !nsec) return set_err(BH_ERR_ARG, "null argument");
+  unsigned long long h[2] = {0, 0};
+  BH_CUDA(cudaMemcpy(h, e->counters, sizeof(h), cudaMemcpyDeviceToHost));
+  nsec[0] = (long long)h[0];
+  nsec[1] = (long long)h[1];
+  return BH_OK;
+}
+
+// ---------------------------------------------------------------------------
+// single-model shims (reference FFI semantics, host pointers)
+// ---------------------------------------------------------------------------
+namespace {
+struct Shim {
+  std::mutex mu;
+  bool ready = false;
+  LayerRow* rows = nullptr;
+  double* periods = nullptr;
+  double* curve = nullptr;
+  int* nlay = nullptr;
+  int* tstatus = nullptr;
+  double* model6 = nullptr;      // z, vp, vs, rho, qp, qs  (6 x 100)
+  RfLayer* rf_lay = nullptr;
+  cm2* rf_coef = nullptr;
+  double* rf_mc = nullptr;
+  cd* spec = nullptr;
+  double* trace = nullptr;
+  int spec_cap = 0;
+  cudaStream_t st = nullptr;
+};
+Shim g_shim;
+
+int shim_init() {
+  if (g_shim.ready) return BH_OK;
+  if (bh_device_count() < 1)
+    return set_err(BH_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+  BH_CUDA(cudaMalloc((void**)&g_shim.rows, sizeof(LayerRow) * 101));
+  BH_CUDA(cudaMalloc((void**)&g_shim.periods, sizeof(double) * BH_MAX_PERIODS));
+  BH_CUDA(cudaMalloc((void**)&g_shim.curve, sizeof(double) * BH_MAX_PERIODS));
+  BH_CUDA(cudaMalloc((void**)&g_shim.nlay, sizeof(int)));
+  BH_CUDA(cudaMalloc((void**)&g_shim.tstatus, sizeof(int) * kMaxTargets));
+  BH_CUDA(cudaMalloc((void**)&g_shim.model6, sizeof(double) * 6 * BH_MAX_LAYERS));
+  BH_CUDA(cudaMalloc((void**)&g_shim.rf_lay, sizeof(RfLayer) * BH_MAX_LAYERS));
+  BH_CUDA(cudaMalloc((void**)&g_shim.rf_coef, sizeof(cm2) * 4 * BH_MAX_LAYERS));
+  BH_CUDA(cudaMalloc((void**)&g_shim.rf_mc, sizeof(double) * 16));
+  BH_CUDA(cudaStreamCreateWithFlags(&g_shim.st, cudaStreamNonBlocking));
+  g_shim.ready = true;
+  return BH_OK;
+}
+}  // namespace
+
+int bh_surfdisp96(const float* thkm, const float* vpm, const float* vsm, const float* rhom,
+                  int nlayer, int iflsph, int iwave, int mode, int igr, int kmax, const double* t,
+                  double* cg, int* err) {
+  if (!thkm || !vpm || !vsm || !rhom || !t || !cg || !err) return set_err(BH_ERR_ARG, "null argument");
+  if (nlayer < 1 || nlayer > BH_MAX_LAYERS || kmax < 1 || kmax > BH_MAX_PERIODS)
+    return set_err(BH_ERR_ARG, "nlayer must be 1..100 and kmax 1..60");
+  if (iwave != 1 && iwave != 2) return set_err(BH_ERR_ARG, "iwave must be 1 (Love) or 2 (Rayleigh)");
+  if (mode != 1) return set_err(BH_ERR_UNSUPPORTED, "only mode = 1 (fundamental) is implemented");
+  if (iflsph != 0) return set_err(BH_ERR_UNSUPPORTED, "only iflsph = 0 (flat earth) is implemented");
+  std::lock_guard<std::mutex> lock(g_shim.mu);
+  int rc = shim_init();
+  if (rc != BH_OK) return rc;
+  Shim& s = g_shim;
+  std::vector<LayerRow> rows(nlayer);
+  for (int i = 0; i < nlayer; ++i) { rows[i].x = thkm[i]; rows[i].y = vpm[i]; rows[i].z = vsm[i]; rows[i].w = rhom[i]; }
+  BH_CUDA(cudaMemcpyAsync(s.rows, rows.data(), sizeof(LayerRow) * nlayer, cudaMemcpyHostToDevice, s.st));
+  BH_CUDA(cudaMemcpyAsync(s.periods, t, sizeof(double) * kmax, cudaMemcpyHostToDevice, s.st));
+  BH_CUDA(cudaMemcpyAsync(s.nlay, &nlayer, sizeof(int), cudaMemcpyHostToDevice, s.st));
+  BH_CUDA(cudaMemsetAsync(s.curve, 0, sizeof(double) * BH_MAX_PERIODS, s.st));
+  SwdLaunch sw{};
+  sw.rows = s.rows; sw.row_stride = odd_stride(nlayer); sw.nlay = s.nlay; sw.B = 1; sw.ncurves = 1;
+  sw.target_id[0] = 0; sw.wave[0] = iwave; sw.igr[0] = igr > 0 ? 1 : 0; sw.kmax[0] = kmax;
+  sw.periods[0] = s.periods; sw.curves = s.curve; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
+  sw.tstatus = s.tstatus; sw.counters = nullptr; sw.searches_per_warp = 1; sw.max_spec = 32;
+  launch_swd(sw, s.st);
+  int ok = 0;
+  std::vector<double> out(kmax);
+  BH_CUDA(cudaMemcpyAsync(out.data(), s.curve, sizeof(double) * kmax, cudaMemcpyDeviceToHost, s.st));
+  BH_CUDA(cudaMemcpyAsync(&ok, s.tstatus, sizeof(int), cudaMemcpyDeviceToHost, s.st));
+  BH_CUDA(cudaStreamSynchronize(s.st));
+  BH_CUDA(cudaGetLastError());
+  *err = ok ? 0 : 1;
+  for (int k = 0; k < kmax; ++k) cg[k] = out[k];
+  return BH_OK;
+}
+
+int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a, double nsv, double sigma,
+             int waveno, int nlay, const double* z, const double* vp, const double* vs,
+             const double* rh, const double* qp, const double* qs, double* fz, double* fr,
+             double* rf) {
+  if (!z || !vp || !vs || !rh || !qp || !qs || !rf) return set_err(BH_ERR_ARG, "null argument");
+  if (nlay < 2 || nlay > BH_MAX_LAYERS) return set_err(BH_ERR_ARG, "nlay must be 2..100");
+  if (nsamp < 2 || (nsamp & (nsamp - 1))) return set_err(BH_ERR_ARG, "nsamp must be a power of two");
+  if (waveno != 0 && waveno != 1) return set_err(BH_ERR_UNSUPPORTED, "waveno must be 0 (P) or 1 (SV)");
+  std::lock_guard<std::mutex> lock(g_shim.mu);
+  int rc = shim_init();
+  if (rc != BH_OK) return rc;
+  Shim& s = g_shim;
+  const int nfreq = nsamp / 2 + 1;
+  if (nfreq > s.spec_cap) {
+    if (s.spec) { cudaFree(s.spec); cudaFree(s.trace); s.spec = nullptr; s.trace = nullptr; s.spec_cap = 0; }
+    BH_CUDA(cudaMalloc((void**)&s.spec, sizeof(cd) * nfreq));
+    BH_CUDA(cudaMalloc((void**)&s.trace, sizeof(double) * nsamp));
+    s.spec_cap = nfreq;
+  }
+  const double* src[6] = {z, vp, vs, rh, qp, qs};
+  for (int k = 0; k < 6; ++k)
+    BH_CUDA(cudaMemcpyAsync(s.model6 + k * BH_MAX_LAYERS, src[k], sizeof(double) * nlay, cudaMemcpyHostToDevice, s.st));
+  BH_CUDA(cudaMemcpyAsync(s.nlay, &nlay, sizeof(int), cudaMemcpyHostToDevice, s.st));
+  PrepOut prep{};
+  prep.rf_lay = s.rf_lay; prep.rf_coef = s.rf_coef; prep.rf_mc = s.rf_mc;
+  double* m = s.model6;
+  launch_prepare_rf_explicit(m, m + BH_MAX_LAYERS, m + 2 * BH_MAX_LAYERS, m + 3 * BH_MAX_LAYERS,
+                             m + 4 * BH_MAX_LAYERS, m + 5 * BH_MAX_LAYERS, nlay, p, nsv, sigma, prep, s.st);
+  RfLaunch rfl{};
+  rfl.lay = s.rf_lay; rfl.coef = s.rf_coef; rfl.mc = s.rf_mc; rfl.nlay = s.nlay; rfl.B = 1; rfl.lmax = nlay;
+  rfl.k.dw = 2.0 * RF_PI * fsamp / nsamp; rfl.k.wref = 2.0 * RF_PI; rfl.k.a = a; rfl.k.tshift = tshift;
+  rfl.k.qn = sqrt(RF_PI) * fsamp / a; rfl.k.u = p * RF_DEG_PER_KM; rfl.k.waveno = waveno; rfl.k.nsamp = nsamp;
+  rfl.spec = s.spec; rfl.out = s.trace; rfl.out_stride = nsamp; rfl.out_off = 0; rfl.ndata = nsamp;
+  rfl.tstatus = nullptr; rfl.target_id = 0;
+  launch_rf_spectrum(rfl, s.st);
+  launch_rf_synth(rfl, s.st);
+  BH_CUDA(cudaMemcpyAsync(rf, s.trace, sizeof(double) * nsamp, cudaMemcpyDeviceToHost, s.st));
+  BH_CUDA(cudaStreamSynchronize(s.st));
+  BH_CUDA(cudaGetLastError());
+  if (fz) memset(fz, 0, sizeof(double) * nsamp);
+  if (fr) memset(fr, 0, sizeof(double) * nsamp);
+  return BH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,529 @@
+// swd_core.cuh -- surface-wave dispersion core (Rayleigh/Love secular functions
+// and the SURF96 root search) written from scratch for the B200 engine.
+//
+// Behavioural reference: src/extensions/surfdisp96.f of BayHunter
+//   secular functions  dltar1 (:710-769), dltar4 (:773-871), var (:874-991),
+//                      dnka (:1024-1068), normc (:995-1020)
+//   root search        surfdisp96 period loop (:223-311), getsol (:390-482),
+//                      nevill (:557-674), half (:676-686), gtsolh (:367-388)
+//
+// Design (not a port): the reference interleaves control flow and secular-
+// function evaluations in nested loops.  Here the search is an explicit state
+// machine ("Search") that only ever *requests* phase-velocity candidates and
+// *consumes* secular values, so that all 32 lanes of a warp always execute the
+// expensive secular function together, and so that spare lanes can evaluate the
+// next bracket candidates c1+dc, c1+2dc, ... speculatively.  The sequence of
+// candidates consumed is exactly the reference's, independent of how many are
+// evaluated per round, hence results do not depend on the lane allocation.
+#pragma once
+#include "bh_common.cuh"
+
+namespace bh {
+
+constexpr int SWD_MAX_PERIODS = 60;   // NP, surfdisp96.f:62
+constexpr int SWD_MAX_LAYERS = 100;   // NL, surfdisp96.f:60
+
+// One layer row of the REAL*4 model the reference sees after the f2py cast
+// (surfdisp96.f:82): x = thickness d, y = vp (a), z = vs (b), w = rho.
+#if defined(__CUDACC__)
+typedef float4 LayerRow;
+#else
+typedef f4 LayerRow;
+#endif
+
+// ---------------------------------------------------------------------------
+// Love secular function: Haskell 2-vector from the half-space to the surface.
+// rows[l*stride], l = 0..L-1, l = L-1 is the half-space.
+// ---------------------------------------------------------------------------
+BH_HD double secular_love(const LayerRow* rows, int stride, int L, double wvno, double omega) {
+  LayerRow hs = rows[(L - 1) * stride];
+  double beta1 = (double)hs.z;
+  double rho1 = (double)hs.w;
+  double xkb = omega / beta1;
+  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double e1 = rho1 * rb;
+  double e2 = 1.0 / (beta1 * beta1);
+  for (int l = L - 2; l >= 0; --l) {
+    LayerRow r = rows[l * stride];
+    double d = (double)r.x;
+    beta1 = (double)r.z;
+    rho1 = (double)r.w;
+    double xmu = rho1 * beta1 * beta1;
+    xkb = omega / beta1;
+    rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    double q = d * rb;
+    double cosq, y, z;
+    if (wvno < xkb) {
+      double sinq;
+      sincos_d(q, &sinq, &cosq);
+      y = sinq / rb;
+      z = -rb * sinq;
+    } else if (wvno == xkb) {
+      cosq = 1.0;
+      y = d;
+      z = 0.0;
+    } else {
+      double fac = (q < 16.0) ? exp(-2.0 * q) : 0.0;
+      cosq = (1.0 + fac) * 0.5;
+      double sinq = (1.0 - fac) * 0.5;
+      y = sinq / rb;
+      z = rb * sinq;
+    }
+    double e10 = e1 * cosq + e2 * xmu * z;
+    double e20 = e1 * y / xmu + e2 * cosq;
+    double xnor = fmax(fabs(e10), fabs(e20));
+    if (xnor < 1.0e-40) xnor = 1.0;
+    // true divisions: when |e10| is the maximum the reference gets exactly
+    // +-1.0, and nevill's sign/ratio tests (:619,:628) sit on that tie.
+    e1 = e10 / xnor;
+    e2 = e20 / xnor;
+  }
+  return e1;
+}
+
+// ---------------------------------------------------------------------------
+// Rayleigh secular function: Dunkin 5-component compound vector propagated
+// from the half-space up; per layer the eigenfunction products of `var` and
+// the compound matrix of `dnka` are formed in registers.
+// ---------------------------------------------------------------------------
+BH_HD double secular_rayleigh(const LayerRow* rows, int stride, int L, double wvno, double omga) {
+  double omega = (omga < 1.0e-4) ? 1.0e-4 : omga;
+  double wvno2 = wvno * wvno;
+  double e0, e1, e2, e3, e4;
+  {
+    LayerRow hs = rows[(L - 1) * stride];
+    double a = (double)hs.y, b = (double)hs.z, rho1 = (double)hs.w;
+    double xka = omega / a, xkb = omega / b;
+    double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    double t = b / omega;
+    double gammk = 2.0 * t * t;
+    double gam = gammk * wvno2;
+    double gamm1 = gam - 1.0;
+    e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
+    e1 = -rho1 * ra;
+    e2 = rho1 * (gamm1 - gammk * ra * rb);
+    e3 = rho1 * rb;
+    e4 = wvno2 - ra * rb;
+  }
+  for (int l = L - 2; l >= 0; --l) {
+    LayerRow r = rows[l * stride];
+    double dpth = (double)r.x, a = (double)r.y, b = (double)r.z, rho = (double)r.w;
+    double xka = omega / a, xkb = omega / b;
+    double t = b / omega;
+    double gammk = 2.0 * t * t;
+    double gam = gammk * wvno2;
+    double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    double p = ra * dpth, q = rb * dpth;
+    // --- var (:921-990) ---
+    double pex = 0.0, sex = 0.0;
+    double cosp, w, x, cosq, y, z;
+    if (wvno < xka) {
+      double sinp;
+      sincos_d(p, &sinp, &cosp);
+      w = sinp / ra;
+      x = -ra * sinp;
+    } else if (wvno == xka) {
+      cosp = 1.0; w = dpth; x = 0.0;
+    } else {
+      pex = p;
+      double fac = (p < 16.0) ? exp(-2.0 * p) : 0.0;
+      cosp = (1.0 + fac) * 0.5;
+      double sinp = (1.0 - fac) * 0.5;
+      w = sinp / ra;
+      x = ra * sinp;
+    }
+    if (wvno < xkb) {
+      double sinq;
+      sincos_d(q, &sinq, &cosq);
+      y = sinq / rb;
+      z = -rb * sinq;
+    } else if (wvno == xkb) {
+      cosq = 1.0; y = dpth; z = 0.0;
+    } else {
+      sex = q;
+      double fac = (q < 16.0) ? exp(-2.0 * q) : 0.0;
+      cosq = (1.0 + fac) * 0.5;
+      double sinq = (1.0 - fac) * 0.5;
+      y = sinq / rb;
+      z = rb * sinq;
+    }
+    double exa = pex + sex;
+    double a0 = (exa < 60.0) ? exp(-exa) : 0.0;
+    double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
+    double xy = x * y, xz = x * z, wy = w * y, wz = w * z;
+    // --- dnka (:1032-1067) ---
+    double gamm1 = gam - 1.0;
+    double twgm1 = gam + gamm1;
+    double gmgmk = gam * gammk;
+    double gmgm1 = gam * gamm1;
+    double gm1sq = gamm1 * gamm1;
+    double rho2 = rho * rho;
+    double rinv = 1.0 / rho;
+    double a0pq = a0 - cpcq;
+    double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
+    double c12 = (wvno2 * cpy - cqx) * rinv;
+    double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * rinv;
+    double c14 = (cpz - wvno2 * cqw) * rinv;
+    double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * (rinv * rinv);
+    double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
+    double c22 = cpcq;
+    double c23 = gammk * cpz - gamm1 * cqw;
+    double c24 = -wz;
+    double c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
+    double c42 = -xy;
+    double c43 = gamm1 * cpy - gammk * cqx;
+    double c51 = -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
+    double c53 = -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
+    double tt = -2.0 * wvno2;
+    double c31 = tt * c53, c32 = tt * c43, c33 = a0 + 2.0 * (cpcq - c11), c34 = tt * c23, c35 = tt * c13;
+    // remaining entries by symmetry (:1048-1060): c25=c14, c44=c22, c45=c12,
+    // c52=c41, c54=c21, c55=c11
+    // --- ee = e * ca (:838-844) ---
+    double n0 = e0 * c11 + e1 * c21 + e2 * c31 + e3 * c41 + e4 * c51;
+    double n1 = e0 * c12 + e1 * c22 + e2 * c32 + e3 * c42 + e4 * c41;
+    double n2 = e0 * c13 + e1 * c23 + e2 * c33 + e3 * c43 + e4 * c53;
+    double n3 = e0 * c14 + e1 * c24 + e2 * c34 + e3 * c22 + e4 * c21;
+    double n4 = e0 * c15 + e1 * c14 + e2 * c35 + e3 * c12 + e4 * c11;
+    // --- normc (:1004-1014); the stored log is never read by the caller ---
+    double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
+    if (t1 < 1.0e-40) t1 = 1.0;
+    // e0 is what the caller finally reads: keep the reference's true division so
+    // that a saturated component is exactly +-1.0 (see secular_love).
+    double inv = 1.0 / t1;
+    e0 = n0 / t1; e1 = n1 * inv; e2 = n2 * inv; e3 = n3 * inv; e4 = n4 * inv;
+  }
+  return e0;
+}
+
+BH_HD double secular(int wave /*1 Love, 2 Rayleigh*/, const LayerRow* rows, int stride, int L,
+                     double wvno, double omega) {
+  return wave == 1 ? secular_love(rows, stride, L, wvno, omega)
+                   : secular_rayleigh(rows, stride, L, wvno, omega);
+}
+
+// ---------------------------------------------------------------------------
+// gtsolh (:367-388): five REAL*4 Newton steps on the half-space Rayleigh
+// equation; every operation individually rounded (no FMA).
+// ---------------------------------------------------------------------------
+BH_HD float halfspace_start(float a, float b) {
+  float c = fmul(0.95f, b);
+  for (int i = 0; i < 5; ++i) {
+    float gamma = fdiv(b, a);
+    float kappa = fdiv(c, b);
+    float k2 = fmul(kappa, kappa);
+    float gk = fmul(gamma, kappa);
+    float gk2 = fmul(gk, gk);
+    float fac1 = fsqrt(fsub(1.0f, gk2));
+    float fac2 = fsqrt(fsub(1.0f, k2));
+    float tk = fsub(2.0f, k2);
+    float fr = fsub(fmul(tk, tk), fmul(fmul(4.0f, fac1), fac2));
+    float t1 = fmul(fmul(-4.0f, tk), kappa);
+    float t2 = fdiv(fmul(fmul(fmul(fmul(4.0f, fac2), gamma), gamma), kappa), fac1);
+    float t3 = fdiv(fmul(fmul(4.0f, fac1), kappa), fac2);
+    float frp = fadd(fadd(t1, t2), t3);
+    frp = fdiv(frp, b);
+    c = fsub(c, fdiv(fr, frp));
+  }
+  return c;
+}
+
+// ---------------------------------------------------------------------------
+// Search state machine
+// ---------------------------------------------------------------------------
+enum SearchStage : int {
+  ST_BR_FIRST = 0,   // waiting for del1 = secular(c1)             (getsol :429)
+  ST_BR_STEP = 1,    // waiting for del2 at c2 = c1 +- dc           (getsol :448-470)
+  ST_RF_TOP = 2,     // waiting for del3; resume at nevill label 100 (:587)
+  ST_RF_POST = 3,    // waiting for del3 of the range-fix half (:596); resume at :599
+  ST_DONE = 4,       // all periods found
+  ST_FAILED = 5      // err = 1 (no root for a period of the fundamental mode)
+};
+
+struct Search {
+  // per-search constants
+  double cc, dc, betmx;      // start value, dble(0.005f), dble(REAL*4 max vs)
+  int wave, igr, kmax;
+  // period bookkeeping
+  int k;                     // 0-based period index
+  int second;                // 0: root at t1 (t1a for group), 1: root at t1b
+  int stage;
+  int ifirst, idir;
+  float t1a, t1b;
+  double omega;              // twopi / t1 of the root being searched
+  double c1, c2, del1, del2, clow, del1st;
+  double cprev;              // c(k-1)
+  double ck;                 // c(k), first root of the current period
+  // nevill
+  double c3, del3;
+  int nev, nctrl, m;
+  double x[11], y[11];
+};
+
+constexpr double SWD_TWOPI = 2.0 * 3.141592653589793;
+
+// Extremal velocities + start value (surfdisp96.f:139-156, 197-217).  Water
+// layers (vs <= 0.01) are outside this engine's scope: vs > 0 is enforced by
+// BayHunter's priors (SingleChain.py:358-363); such a model is reported failed.
+BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int wave, int igr, int kmax) {
+  float betmx = -1.e20f, betmn = 1.e20f;
+  int jmn = 0;
+  bool solid = true;
+  for (int i = 0; i < L; ++i) {
+    LayerRow r = rows[i * stride];
+    if (r.z > 0.01f && r.z < betmn) { betmn = r.z; jmn = i; }
+    else if (r.z <= 0.01f) solid = false;
+    if (r.z > betmx) betmx = r.z;
+  }
+  s.wave = wave; s.igr = igr; s.kmax = kmax;
+  s.dc = fabs((double)0.005f);
+  s.betmx = (double)betmx;
+  s.k = 0; s.second = 0;
+  s.cprev = 0.0; s.ck = 0.0; s.del1st = 0.0;
+  s.t1a = 0.f; s.t1b = 0.f; s.omega = 0.0;
+  s.c1 = s.c2 = s.del1 = s.del2 = s.clow = 0.0;
+  s.c3 = s.del3 = 0.0; s.nev = 0; s.nctrl = 0; s.m = 0;
+  s.ifirst = 0; s.idir = 1;
+  if (!solid || L < 1 || kmax < 1) { s.cc = 0.0; s.stage = ST_FAILED; return false; }
+  LayerRow rm = rows[jmn * stride];
+  float cc1 = halfspace_start(rm.y, rm.z);
+  cc1 = fmul(.95f, cc1);
+  cc1 = fmul(.90f, cc1);
+  s.cc = (double)cc1;
+  s.stage = ST_BR_FIRST;
+  return true;
+}
+
+// Start the search for period index s.k (first root).  period = t(k).
+BH_HD void search_begin_period(Search& s, double period) {
+  double t1 = period;
+  if (s.igr > 0) {
+    // t1a = t1/(1.+h), t1b = t1/(1.-h): REAL*4 sums, REAL*8 quotient, REAL*4 store (:233-235)
+    s.t1a = (float)(t1 / (double)fadd(1.0f, 0.005f));
+    s.t1b = (float)(t1 / (double)fsub(1.0f, 0.005f));
+    t1 = (double)s.t1a;
+  } else {
+    s.t1a = (float)t1;
+    s.t1b = 0.0f;
+  }
+  s.second = 0;
+  if (s.k == 0) {            // :253-256
+    s.c1 = s.cc; s.clow = s.cc; s.ifirst = 1;
+  } else {                   // :268-271
+    s.ifirst = 0;
+    s.c1 = dadd(s.cprev, -dmul(1.5, s.dc));
+    s.clow = s.cc;           // clow = cm = cc
+  }
+  s.omega = SWD_TWOPI / t1;
+  s.stage = ST_BR_FIRST;
+}
+
+// Next bracket candidate of getsol's loop (:448-458), advancing (c1, idir).
+BH_HD double bracket_next(double& c1, int& idir, double clow, double dc) {
+  double c2 = (idir > 0) ? c1 + dc : c1 - dc;
+  if (c2 <= clow) {
+    idir = +1;
+    c1 = clow;
+    c2 = c1 + dc;
+  }
+  return c2;
+}
+
+// How many candidates the search can use this round (>= 1 while running).
+BH_HD int search_nwant(const Search& s, int nmax) {
+  if (s.stage >= ST_DONE) return 0;
+  return s.stage == ST_BR_STEP ? nmax : 1;
+}
+
+// i-th pending candidate (i = 0 is the one the reference evaluates next).
+// The published (stage, c, idir, clow) tuple is all a worker lane needs.
+BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i) {
+  if (stage != ST_BR_STEP) return c;     // c1 (BR_FIRST) or c3 (refine)
+  double c1 = c, c2 = c;
+  for (int j = 0; j <= i; ++j) {
+    c2 = bracket_next(c1, idir, clow, dc);
+    c1 = c2;
+  }
+  return c2;
+}
+BH_HD double search_pending_c(const Search& s) {
+  return (s.stage == ST_BR_FIRST || s.stage == ST_BR_STEP) ? s.c1 : s.c3;
+}
+
+// ---- nevill pieces -------------------------------------------------------
+BH_HD void nevill_request_half(Search& s, int next_stage) {
+  s.c3 = 0.5 * (s.c1 + s.c2);
+  s.stage = next_stage;
+}
+
+// Called when a root c3 has been accepted by nevill (:671-673) and getsol's
+// post-checks (:475-476) are due.  Returns true when the whole curve is done
+// or failed; `out` receives cg(k) when a period completes (out_valid = true).
+BH_HD void search_root_done(Search& s, const double* periods, double* out, bool* out_valid) {
+  double c1 = s.c3;
+  bool ok = !(c1 > s.betmx);                       // :476
+  *out_valid = false;
+  if (s.second == 0) {
+    if (!ok) { s.stage = ST_FAILED; return; }      // :277 -> 1700, err = 1
+    s.ck = c1;                                     // c(k) = c1
+    if (s.igr > 0) {                               // :282-287 second root at t1b
+      s.second = 1;
+      s.ifirst = 0;
+      s.clow = dmul(1.0e-2, s.dc);                // cb(k) + one*dc, cb(k) = 0 in the fundamental mode
+      s.c1 = dadd(c1, -dmul(1.5, s.dc));
+      s.omega = SWD_TWOPI / (double)s.t1b;
+      s.stage = ST_BR_FIRST;
+      return;
+    }
+    *out = (double)(float)s.ck;                    // cg(k) = sngl(c(k)) (:298,303)
+    *out_valid = true;
+  } else {
+    if (!ok) c1 = s.ck;                            // :291-293
+    float cc0 = (float)s.ck, cc1 = (float)c1;
+    // :306 evaluated entirely in REAL*4, each operation rounded
+    float num = fsub(fdiv(1.0f, s.t1a), fdiv(1.0f, s.t1b));
+    float den = fsub(fdiv(1.0f, fmul(s.t1a, cc0)), fdiv(1.0f, fmul(s.t1b, cc1)));
+    *out = (double)fdiv(num, den);
+    *out_valid = true;
+  }
+  // next period
+  s.cprev = s.ck;
+  s.k += 1;
+  if (s.k >= s.kmax) { s.stage = ST_DONE; return; }
+  search_begin_period(s, periods[s.k]);
+}
+
+// Failure inside getsol's bracket loop (:468-469 -> 1700).
+BH_HD void search_bracket_failed(Search& s, const double* periods, double* out, bool* out_valid) {
+  *out_valid = false;
+  if (s.second == 0) { s.stage = ST_FAILED; return; }
+  // second root of a group-velocity period not found: reuse c(k) (:291-293)
+  s.c3 = s.ck;
+  // betmx check was on getsol's own root; here c1 = c(k) unconditionally
+  float cc0 = (float)s.ck, cc1 = (float)s.ck;
+  float num = fsub(fdiv(1.0f, s.t1a), fdiv(1.0f, s.t1b));
+  float den = fsub(fdiv(1.0f, fmul(s.t1a, cc0)), fdiv(1.0f, fmul(s.t1b, cc1)));
+  *out = (double)fdiv(num, den);
+  *out_valid = true;
+  s.cprev = s.ck;
+  s.k += 1;
+  if (s.k >= s.kmax) { s.stage = ST_DONE; return; }
+  search_begin_period(s, periods[s.k]);
+}
+
+// nevill main loop from label 100 (:587) until the next secular evaluation is
+// needed (returns with stage = ST_RF_TOP / ST_RF_POST and c3 set) or the root
+// is accepted (returns true).
+BH_HD bool nevill_resume(Search& s, bool at_top) {
+  for (;;) {
+    if (at_top) {
+      s.nctrl += 1;
+      if (s.nctrl >= 100) return true;                                   // :589
+      if (s.c3 < fmin(s.c1, s.c2) || s.c3 > fmax(s.c1, s.c2)) {          // :594-598
+        s.nev = 0;
+        nevill_request_half(s, ST_RF_POST);
+        return false;
+      }
+    }
+    at_top = true;
+    double s13 = s.del1 - s.del3;
+    double s32 = s.del3 - s.del2;
+    if (sign1(s.del3) * sign1(s.del1) < 0.0) { s.c2 = s.c3; s.del2 = s.del3; }   // :604-610
+    else { s.c1 = s.c3; s.del1 = s.del3; }
+    if (fabs(s.c1 - s.c2) <= 1.0e-6 * s.c1) return true;                 // :614
+    if (sign1(s13) != sign1(s32)) s.nev = 0;                             // :619
+    double ss1 = fabs(s.del1);
+    double s1 = (double)0.01f * ss1;                                     // REAL*4 literal (:625)
+    double ss2 = fabs(s.del2);
+    double s2 = (double)0.01f * ss2;
+    if (s1 > ss2 || s2 > ss1 || s.nev == 0) {                            // :628-632
+      nevill_request_half(s, ST_RF_TOP);
+      s.nev = 1;
+      s.m = 1;
+      return false;
+    }
+    if (s.nev == 2) {                                                    // :634-643
+      s.x[s.m] = s.c3;
+      s.y[s.m] = s.del3;
+    } else {
+      s.x[0] = s.c1; s.y[0] = s.del1;
+      s.x[1] = s.c2; s.y[1] = s.del2;
+      s.m = 1;
+    }
+    bool bad = false;
+    for (int kk = 1; kk <= s.m; ++kk) {                                  // :649-654
+      int j = s.m - kk;
+      double denom = s.y[s.m] - s.y[j];
+      if (fabs(denom) < 1.0e-10 * fabs(s.y[s.m])) { bad = true; break; }
+      s.x[j] = (-s.y[j] * s.x[j + 1] + s.y[s.m] * s.x[j]) / denom;
+    }
+    if (bad) {                                                           // :663-667
+      nevill_request_half(s, ST_RF_TOP);
+      s.nev = 1;
+      s.m = 1;
+      return false;
+    }
+    s.c3 = s.x[0];                                                       // :655-661
+    s.nev = 2;
+    s.m = s.m + 1;
+    if (s.m > 10) s.m = 10;
+    s.stage = ST_RF_TOP;
+    return false;
+  }
+}
+
+// Consume n secular values del[0..n) for the candidates this search published
+// this round (n = 1 unless stage == ST_BR_STEP).  `periods` is the period
+// vector of the curve; finished velocities are stored through `emit(k, value)`.
+// Returns how many of the n values were consumed (the rest was speculation
+// past a sign change or past the search window).
+template <class Emit>
+BH_HD int search_consume(Search& s, const double* del, int n, const double* periods, Emit emit) {
+  double out = 0.0;
+  bool out_valid = false;
+  int kdone = s.k;
+  switch (s.stage) {
+    case ST_BR_FIRST: {
+      s.del1 = del[0];
+      if (s.ifirst == 1) s.del1st = s.del1;                              // :430
+      double plmn = sign1(s.del1st) * sign1(s.del1);
+      s.idir = (s.ifirst == 1 || plmn >= 0.0) ? +1 : -1;                 // :432-438
+      s.stage = ST_BR_STEP;
+      return 1;
+    }
+    case ST_BR_STEP: {
+      for (int i = 0; i < n; ++i) {
+        s.c2 = bracket_next(s.c1, s.idir, s.clow, s.dc);
+        s.del2 = del[i];
+        if (sign1(s.del1) != sign1(s.del2)) {                            // :462 -> nevill
+          nevill_request_half(s, ST_RF_TOP);                             // :583
+          s.nev = 1;
+          s.nctrl = 1;
+          return i + 1;
+        }
+        s.c1 = s.c2;
+        s.del1 = s.del2;
+        if (s.c1 < s.cc || s.c1 >= (s.betmx + s.dc)) {                   // :468-469 (cm = cc)
+          search_bracket_failed(s, periods, &out, &out_valid);
+          if (out_valid) emit(kdone, out);
+          return i + 1;
+        }
+      }
+      return n;
+    }
+    case ST_RF_TOP:
+    case ST_RF_POST: {
+      s.del3 = del[0];
+      if (nevill_resume(s, s.stage == ST_RF_TOP)) {
+        search_root_done(s, periods, &out, &out_valid);
+        if (out_valid) emit(kdone, out);
+      }
+      return 1;
+    }
+    default:
+      return 0;
+  }
+}
+
+}  // namespace bh

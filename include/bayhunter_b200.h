@@ -1,0 +1,176 @@
+/*
+ * bayhunter_b200.h -- C ABI of the B200-native forward-model + likelihood engine
+ * for BayHunter's hot path (libbayhunter_b200.so, sm_100a).
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Device pointers are
+ * whatever the caller owns (e.g. torch.Tensor.data_ptr()); the library never
+ * allocates caller-visible memory and keeps no caller pointer after a call
+ * returns (same ownership rule as the reference FFI).  Internal
+ * scratch lives inside the opaque engine handle.
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * BayHunter tree):
+ *
+ *   bh_surfdisp96        <- Fortran `surfdisp96` called through f2py
+ *                           (src/extensions/surfdisp96.f:55-56, called from
+ *                           src/surf96_modsw.py:116-117)
+ *   bh_synrf             <- extern "C" `synrf_cwrap`
+ *                           (src/extensions/rfmini/wrap.cpp:57-80, called from
+ *                           src/extensions/rfmini/rfmini.pyx:111-112 and
+ *                           src/rfmini_modrf.py:134-137)
+ *   bh_engine_eval       <- the per-chain, per-iteration body of
+ *                           JointTarget.evaluate (src/Targets.py:314-347) incl.
+ *                           Model.get_vp_vs_h's vp rule (src/Models.py:40-52),
+ *                           the plugins' run_model (src/surf96_modsw.py:84-126,
+ *                           src/rfmini_modrf.py:99-154) and the covariance laws
+ *                           (src/Targets.py:105-183), for B chains per call
+ *   bh_engine_eval_host  <- same, host buffers in / host buffers out (what a
+ *                           ctypes / cgo / JNI binding with numpy-like arrays calls)
+ *
+ * All functions return BH_OK (0) or a negative error code; no exceptions and no
+ * process exit cross this boundary.  Numerical failure is reported in-band the
+ * way the reference does: status[b] = 0, logL[b] = -1e15, misfits[b][*] = 1e15
+ * (src/Targets.py:325-328).
+ */
+#ifndef BAYHUNTER_B200_H
+#define BAYHUNTER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH_ABI_VERSION 1
+#define BH_MAX_TARGETS 8
+#define BH_MAX_PERIODS 60    /* NP, surfdisp96.f:62 */
+#define BH_MAX_LAYERS 100    /* NL, surfdisp96.f:60 */
+
+/* error codes */
+#define BH_OK 0
+#define BH_ERR_ARG (-1)          /* bad argument (null pointer, size out of range) */
+#define BH_ERR_CUDA (-2)         /* CUDA runtime error; see bh_last_error() */
+#define BH_ERR_UNSUPPORTED (-3)  /* feature outside this engine's scope */
+#define BH_ERR_NO_DEVICE (-4)    /* no CUDA device: this library has no CPU path */
+
+/* target kinds: BayHunter `ref` strings (src/Targets.py:52-53) */
+#define BH_REF_RDISPPH 0
+#define BH_REF_RDISPGR 1
+#define BH_REF_LDISPPH 2
+#define BH_REF_LDISPGR 3
+#define BH_REF_PRF 4
+#define BH_REF_SRF 5
+
+/* covariance laws bound per target at chain init (src/SingleChain.py:159-205) */
+#define BH_COV_EXP 0            /* Valuation.get_covariance_exp              */
+#define BH_COV_WHITE 1          /* Valuation.get_covariance_nocorr           */
+#define BH_COV_WHITE_SCALED 2   /* Valuation.get_covariance_nocorr_scalederr */
+#define BH_COV_GAUSS 3          /* Valuation.get_covariance_gauss            */
+
+/* One observed data set + its forward-model parameters.  All pointers are
+ * HOST pointers, read during bh_engine_create only. */
+typedef struct bh_target {
+  int ref;                 /* BH_REF_*                                        */
+  int n;                   /* number of observed samples                      */
+  const double* x;         /* [n] periods (s) or time axis (s)                */
+  const double* y;         /* [n] observed data                               */
+  const double* yerr;      /* [n] or NULL (only BH_COV_WHITE_SCALED reads it) */
+  int cov;                 /* BH_COV_*                                        */
+  const double* corr_inv;  /* [n*n] row-major R^-1 for BH_COV_GAUSS else NULL */
+  double logcorr_det;      /* slogdet(R) for BH_COV_GAUSS                     */
+  /* SurfDisp.set_modelparams keys (src/surf96_modsw.py:28-31) */
+  int mode;                /* 1 = fundamental (only value supported)          */
+  int flsph;               /* 0 = flat earth (only value supported)           */
+  /* RFminiModRF.set_modelparams keys (src/rfmini_modrf.py:26-31) */
+  double gauss;            /* Gauss parameter a                               */
+  double p;                /* slowness, s/deg                                 */
+  double nsv;              /* near-surface vs for the rotation; <= 0: vs[0]   */
+  double qp, qs;           /* layer-independent Q (<= 0: 500 / 225)           */
+} bh_target;
+
+typedef struct bh_engine bh_engine;
+
+/* Library / device probes (no device work). */
+int bh_abi_version(void);
+const char* bh_last_error(void);
+int bh_device_count(void);
+
+/*
+ * Create an engine for a fixed joint target set.  Uploads observed data,
+ * periods and R^-1 once; allocates scratch for up to max_batch models of up
+ * to max_layers rows (half-space included) on the current CUDA device.
+ */
+int bh_engine_create(const bh_target* targets, int ntargets, int max_batch,
+                     int max_layers, bh_engine** out);
+void bh_engine_destroy(bh_engine* e);
+
+/* Size of one model's synthetic-data row: sum of n over targets. */
+int bh_engine_synth_stride(const bh_engine* e);
+
+/* Tunables (call before eval; all have working defaults).
+ *   key "swd_searches_per_warp"  1..32   (default chosen from the batch size)
+ *   key "swd_max_spec"           1..32   speculative bracket candidates per search
+ *   key "concurrent"             0/1     run SWD and RF kernels on forked streams
+ *   key "profile"                0/1     record per-kernel event timings */
+int bh_engine_set(bh_engine* e, const char* key, int value);
+
+/*
+ * Evaluate B layered models (one per chain), DEVICE pointers.
+ *   model   [B][lmax][4] fp64 rows (vs, vp/vs, z_top, h); rows >= nlay[b] ignored
+ *   nlay    [B] int32, rows per model incl. half-space (h of last row ignored)
+ *   noise   [B][2T] fp64 (corr_0, sigma_0, corr_1, sigma_1, ...)  (Targets.py:335)
+ *   rho     [B][lmax] fp64 or NULL (NULL: rho = 0.32*vp + 0.77, Targets.py:319)
+ *   logL    [B] fp64 out
+ *   misfits [B][T+1] fp64 out (last = joint)
+ *   status  [B] int32 out (1 valid, 0 invalid -> sentinels written)
+ *   synth   [B][synth_stride] fp64 out or NULL (modelled data, targets back to back)
+ *   stream  cudaStream_t (as void*); work is enqueued, not synchronised
+ */
+int bh_engine_eval(bh_engine* e, const double* model, const int* nlay,
+                   const double* noise, const double* rho, int B, int lmax,
+                   double* logL, double* misfits, int* status, double* synth,
+                   void* stream);
+
+/* Same with HOST pointers: pinned staging, H2D, kernels, D2H, one stream
+ * synchronise before returning. */
+int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay,
+                        const double* noise, const double* rho, int B, int lmax,
+                        double* logL, double* misfits, int* status, double* synth);
+
+/* Per-kernel device time of the last eval, measured with CUDA events on the
+ * launching streams; needs bh_engine_set(e, "profile", 1) before that eval.
+ * ms[BH_NUM_KERNELS], index BH_K_*; -1 for kernels that did not run.  With several
+ * RF targets the RF entries hold the last one. Synchronises on the stop events. */
+#define BH_K_PREP_SWD 0
+#define BH_K_SWD 1
+#define BH_K_PREP_RF 2
+#define BH_K_RF_SPECTRUM 3
+#define BH_K_RF_SYNTH 4
+#define BH_K_LOGLIK 5
+#define BH_NUM_KERNELS 6
+int bh_engine_last_kernel_ms(bh_engine* e, float* ms);
+
+/* Secular-function evaluations issued by the last eval: nsec[0] = consumed by
+ * the searches, nsec[1] = evaluated (>= nsec[0] with speculation). Host ints. */
+int bh_engine_last_counts(bh_engine* e, long long* nsec);
+
+/*
+ * Single-model shims with the argument meaning of the reference FFI (HOST
+ * pointers).  They run the same CUDA kernels with B = 1.
+ *
+ * bh_surfdisp96: thkm/vpm/vsm/rhom REAL*4 [nlayer]; t, cg fp64 [kmax];
+ *   iwave 1 Love / 2 Rayleigh; igr 0 phase / >0 group; *err = 0 ok, 1 no root.
+ * bh_synrf: as synrf_cwrap; fz/fr may be NULL (BayHunter discards them; when
+ *   given they are zero-filled), rf [nsamp]; returns BH_OK instead of 1.
+ */
+int bh_surfdisp96(const float* thkm, const float* vpm, const float* vsm,
+                  const float* rhom, int nlayer, int iflsph, int iwave, int mode,
+                  int igr, int kmax, const double* t, double* cg, int* err);
+int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a,
+             double nsv, double sigma, int waveno, int nlay, const double* z,
+             const double* vp, const double* vs, const double* rh,
+             const double* qp, const double* qs, double* fz, double* fr,
+             double* rf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYHUNTER_B200_H */

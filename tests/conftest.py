@@ -1,0 +1,50 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The CPU checkers (oracle/), built on demand."""
+    from oracle import joint_oracle
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        joint_oracle.build()
+    joint_oracle.lib()
+    return joint_oracle
+
+
+@pytest.fixture(scope="session")
+def host_sim():
+    """Host lock-step simulation of the device cores (tests/host_sim)."""
+    import ctypes
+    src = os.path.join(ROOT, "tests", "host_sim", "core_sim.cpp")
+    so = os.path.join(ROOT, "tests", "host_sim", "libcore_sim.so")
+    deps = [src] + [os.path.join(ROOT, "bayhunter_b200", "csrc", f)
+                    for f in ("bh_common.cuh", "swd_core.cuh", "rf_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                        "-o", so, src, "-lm"], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+def has_cuda():
+    try:
+        from bayhunter_b200 import _lib
+        return _lib.load().bh_device_count() > 0
+    except Exception:
+        return False

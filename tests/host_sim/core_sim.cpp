@@ -1,0 +1,120 @@
+// core_sim.cpp -- TEST INFRASTRUCTURE.  Host-side lock-step simulation of the
+// device cores (bayhunter_b200/csrc/{swd,rf}_core.cuh compiled as plain C++).
+// It lets the CPU test-suite check the search state machine (with arbitrary,
+// even random, speculation widths) and the receiver-function algebra against
+// the oracle without a GPU.  Nothing in the product path links this file.
+#include <complex>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "../../bayhunter_b200/csrc/rf_core.cuh"
+#include "../../bayhunter_b200/csrc/swd_core.cuh"
+
+using namespace bh;
+
+namespace {
+struct Emit {
+  double* dst;
+  void operator()(int k, double v) const { dst[k] = v; }
+};
+uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
+}  // namespace
+
+extern "C" {
+
+// One dispersion curve for one model.  rows: (d, vp, vs, rho) REAL*4 x nlayer.
+// spec_mode: 0 -> one candidate per round (reference order), k > 0 -> fixed k
+// speculative bracket candidates per round, < 0 -> random 1..32 per round.
+// counts[0] consumed, counts[1] evaluated secular values.
+int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, const double* periods,
+                  int spec_mode, unsigned seed, double* cg, long long* counts) {
+  std::vector<LayerRow> rows(nlayer);
+  for (int i = 0; i < nlayer; ++i) {
+    rows[i].x = rows4[4 * i]; rows[i].y = rows4[4 * i + 1];
+    rows[i].z = rows4[4 * i + 2]; rows[i].w = rows4[4 * i + 3];
+  }
+  for (int k = 0; k < kmax; ++k) cg[k] = 0.0;
+  Search s;
+  long long consumed = 0, evaluated = 0;
+  if (search_setup(s, rows.data(), 1, nlayer, wave, igr, kmax)) search_begin_period(s, periods[0]);
+  uint32_t rng = seed;
+  double del[32];
+  while (s.stage < ST_DONE) {
+    int nmax = spec_mode == 0 ? 1 : (spec_mode > 0 ? spec_mode : 1 + (int)(lcg(rng) % 32));
+    int n = search_nwant(s, nmax);
+    double cpub = search_pending_c(s);
+    for (int i = 0; i < n; ++i) {
+      double c = candidate_from(s.stage, cpub, s.idir, s.clow, s.dc, i);
+      del[i] = secular(wave, rows.data(), 1, nlayer, s.omega / c, s.omega);
+      ++evaluated;
+    }
+    consumed += search_consume(s, del, n, periods, Emit{cg});
+  }
+  if (counts) { counts[0] = consumed; counts[1] = evaluated; }
+  return s.stage == ST_DONE ? 0 : 1;   // err like surfdisp96
+}
+
+// Receiver function through rf_core.cuh; same arguments as synrf_cwrap minus fz/fr.
+int rf_sim(int nsamp, double fsamp, double tshift, double p, double a, double nsv, double sigma,
+           int waveno, int nlay, const double* z, const double* vp, const double* vs,
+           const double* rh, const double* qp, const double* qs, double* rf) {
+  if (nlay < 2) return 0;
+  const double u = p * RF_DEG_PER_KM;
+  std::vector<RfLayer> lay(nlay);
+  std::vector<cm2> coef(4 * nlay);
+  std::vector<double> fvp(nlay), fvs(nlay), frho(nlay);
+  const cd zero = mk(0.0, 0.0);
+  for (int i = 0; i < nlay; ++i) {
+    double h = (i < nlay - 1) ? z[i + 1] - z[i] : -1.0;
+    double hf;
+    rf_flatten(z[i], h, vp[i], vs[i], rh[i], &hf, &fvp[i], &fvs[i], &frho[i]);
+    lay[i].h = hf; lay[i].vp = fvp[i]; lay[i].vs = fvs[i]; lay[i].rho = frho[i];
+    lay[i].cqp = 1.0 / (RF_PI * qp[i]); lay[i].bqp = 1.0 / (2.0 * qp[i]);
+    lay[i].cqs = 1.0 / (RF_PI * qs[i]); lay[i].bqs = 1.0 / (2.0 * qs[i]);
+    cm2 rd, td, ru, tu;
+    rd.a11 = rd.a12 = rd.a21 = rd.a22 = zero; td = rd; ru = rd; tu = rd;
+    if (i == 0) rf_coeff_surface(u, fvp[0], fvs[0], &ru);
+    else rf_coeff_interface(u, fvp[i - 1], fvs[i - 1], frho[i - 1], fvp[i], fvs[i], frho[i], &rd, &td, &ru, &tu);
+    coef[4 * i] = rd; coef[4 * i + 1] = td; coef[4 * i + 2] = ru; coef[4 * i + 3] = tu;
+  }
+  cm2 h2;
+  rf_displacement2(u, fvp[0], fvs[0], &h2);
+  double dm[4];
+  bool dec_on = rf_decomp_consts(u, nsv, sigma, dm);
+  RfSpecConsts k;
+  k.dw = 2.0 * RF_PI * fsamp / nsamp; k.wref = 2.0 * RF_PI; k.a = a; k.tshift = tshift;
+  k.qn = sqrt(RF_PI) * fsamp / a; k.u = u; k.waveno = waveno; k.nsamp = nsamp;
+  const int nfreq = nsamp / 2 + 1;
+  std::vector<std::complex<double>> x(nsamp);
+  for (int j = 0; j < nfreq; ++j) {
+    double w = k.dw * j;
+    double lgw = j ? log(w / k.wref) : 0.0;
+    cm2 t = rf_transfer(lay.data(), coef.data(), h2, nlay, u * u, w, lgw);
+    cd v = rf_spectral_value(t, k, dm, dec_on, j);
+    x[j] = std::complex<double>(v.re, v.im);
+  }
+  for (int i = nfreq; i < nsamp; ++i) x[i] = std::conj(x[nsamp - i]);
+  // plain O(N log N) radix-2 inverse transform (sign +1), scale 1/N
+  int logn = 0;
+  while ((1 << logn) < nsamp) ++logn;
+  std::vector<std::complex<double>> y(nsamp);
+  for (int i = 0; i < nsamp; ++i) {
+    int r = 0;
+    for (int bit = 0; bit < logn; ++bit) if (i & (1 << bit)) r |= 1 << (logn - 1 - bit);
+    y[r] = x[i];
+  }
+  for (int l = 1; l < nsamp; l <<= 1)
+    for (int m = 0; m < l; ++m) {
+      std::complex<double> wv = std::polar(1.0, RF_PI * m / l);
+      for (int i = m; i < nsamp; i += 2 * l) {
+        std::complex<double> bb = wv * y[i + l];
+        y[i + l] = y[i] - bb;
+        y[i] += bb;
+      }
+    }
+  for (int i = 0; i < nsamp; ++i) rf[i] = y[i].real() / nsamp;
+  return 1;
+}
+
+}  // extern "C"
