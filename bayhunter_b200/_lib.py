@@ -58,6 +58,7 @@ SIGNATURES = {
     "bh_engine_last_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "bh_surfdisp96": (ctypes.c_int, [c_float_p] * 4 + [ctypes.c_int] * 6 +
                       [c_double_p, c_double_p, c_int_p]),
+    "bh_debug_math": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p]),
     "bh_synrf": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 +
                  [c_double_p] * 9),
 }

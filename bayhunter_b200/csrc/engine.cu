@@ -20,6 +20,7 @@
 
 #include "../../include/bayhunter_b200.h"
 #include "kernels.h"
+#include "bh_math.cuh"
 
 using namespace bh;
 
@@ -541,4 +542,39 @@ int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a, double 
   return BH_OK;
 }
 
+// ---------------------------------------------------------------------------
+// diagnostics: the straight-line elementary functions of bh_math.cuh, evaluated
+// on the device for a host vector (tests compare them with libm)
+// ---------------------------------------------------------------------------
 }  // extern "C"
+
+namespace {
+__global__ void debug_math_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x[i], s, c, sq, rsq;
+  fm::sincos_cw(v, &s, &c);
+  fm::sqrt_rsqrt(fabs(v), &sq, &rsq);
+  out[i] = fm::exp_small(-fabs(v));
+  out[n + i] = s;
+  out[2 * n + i] = c;
+  out[3 * n + i] = fm::rcp(v);
+  out[4 * n + i] = sq;
+  out[5 * n + i] = rsq;
+  out[6 * n + i] = fm::div(1.0, v);
+}
+}  // namespace
+
+extern "C" int bh_debug_math(int n, const double* x, double* out) {
+  if (n < 1 || !x || !out) return set_err(BH_ERR_ARG, "bad argument");
+  if (bh_device_count() < 1) return set_err(BH_ERR_NO_DEVICE, "no CUDA device visible");
+  double *dx = nullptr, *dout = nullptr;
+  BH_CUDA(cudaMalloc((void**)&dx, sizeof(double) * n));
+  BH_CUDA(cudaMalloc((void**)&dout, sizeof(double) * 7 * n));
+  BH_CUDA(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  debug_math_kernel<<<(n + 127) / 128, 128>>>(dx, dout, n);
+  cudaError_t ce = cudaMemcpy(out, dout, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dout);
+  if (ce != cudaSuccess) return set_err(BH_ERR_CUDA, "debug_math", ce);
+  return BH_OK;
+}

@@ -17,6 +17,7 @@
 // evaluated per round, hence results do not depend on the lane allocation.
 #pragma once
 #include "bh_common.cuh"
+#include "bh_math.cuh"
 
 namespace bh {
 
@@ -35,7 +36,7 @@ typedef f4 LayerRow;
 // Love secular function: Haskell 2-vector from the half-space to the surface.
 // rows[l*stride], l = 0..L-1, l = L-1 is the half-space.
 // ---------------------------------------------------------------------------
-BH_HD double secular_love(const LayerRow* rows, int stride, int L, double wvno, double omega) {
+BH_HD double secular_love_reforder(const LayerRow* rows, int stride, int L, double wvno, double omega) {
   LayerRow hs = rows[(L - 1) * stride];
   double beta1 = (double)hs.z;
   double rho1 = (double)hs.w;
@@ -86,7 +87,7 @@ BH_HD double secular_love(const LayerRow* rows, int stride, int L, double wvno, 
 // from the half-space up; per layer the eigenfunction products of `var` and
 // the compound matrix of `dnka` are formed in registers.
 // ---------------------------------------------------------------------------
-BH_HD double secular_rayleigh(const LayerRow* rows, int stride, int L, double wvno, double omga) {
+BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, double wvno, double omga) {
   double omega = (omga < 1.0e-4) ? 1.0e-4 : omga;
   double wvno2 = wvno * wvno;
   double e0, e1, e2, e3, e4;
@@ -197,10 +198,158 @@ BH_HD double secular_rayleigh(const LayerRow* rows, int stride, int L, double wv
   return e0;
 }
 
+// ---------------------------------------------------------------------------
+// Device formulation of the same two functions: identical algebra, but
+//  * branch-free per layer (the oscillatory / evanescent / grazing cases are
+//    selects; a warp mixing them paid for both sides anyway) so that the P and
+//    S halves and the matrix algebra of a layer form one long basic block with
+//    instruction-level parallelism for the fp64 pipe,
+//  * exp(-2p) = exp(-p)^2 and exp(-(p+q)) = exp(-p) exp(-q): two exponentials
+//    per layer instead of three,
+//  * reciprocals and rsqrt seeds instead of IEEE divisions / square roots
+//    (bh_math.cuh), except the LAST normalisation, whose IEEE division keeps a
+//    saturated secular value at exactly +-1.0 like the reference (nevill's
+//    sign/ratio tests sit on that tie, surfdisp96.f:619,628).
+// ---------------------------------------------------------------------------
+struct HalfTerms { double cs, sn_over_r, r_sn, ex; };   // cos-like, sin/r, +-r*sin, exponent
+
+// `var` for one wave type of one layer (surfdisp96.f:929-968): k = wvno, xk = omega/v,
+// s = (k+xk)|k-xk|, d = thickness.  Returns cosp, w = sinp/ra, x = -+ra*sinp and the
+// evanescent exponent pex (0 unless k > xk); *e_out = exp(-p) (1 if not evanescent).
+BH_HD HalfTerms half_terms(double k, double xk, double d, double* e_out) {
+  double s = (k + xk) * fabs(k - xk);
+  double r, ir;
+  fm::sqrt_rsqrt(s, &r, &ir);
+  double p = r * d;
+  double em = fm::exp_small(fmax(-p, -700.0));
+  double sn, cs;
+  fm::sincos_cw(p, &sn, &cs);
+  const bool osc = k < xk, graze = (k == xk);
+  double fac = (p < 16.0) ? em * em : 0.0;
+  HalfTerms h;
+  double sh = osc ? sn : (1.0 - fac) * 0.5;
+  h.cs = osc ? cs : (1.0 + fac) * 0.5;
+  h.sn_over_r = sh * ir;
+  double rs = r * sh;
+  h.r_sn = osc ? -rs : rs;
+  h.ex = osc ? 0.0 : p;
+  *e_out = osc ? 1.0 : em;
+  if (graze) { h.cs = 1.0; h.sn_over_r = d; h.r_sn = 0.0; h.ex = 0.0; *e_out = 1.0; }
+  return h;
+}
+
+BH_HD double secular_love_fast(const LayerRow* rows, int stride, int L, double wvno, double omega) {
+  LayerRow hs = rows[(L - 1) * stride];
+  double beta1 = (double)hs.z;
+  double ib = fm::rcp(beta1);
+  double xkb = omega * ib;
+  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double e1 = (double)hs.w * rb;
+  double e2 = ib * ib;
+  for (int l = L - 2; l >= 0; --l) {
+    LayerRow r = rows[l * stride];
+    double d = (double)r.x;
+    beta1 = (double)r.z;
+    double xmu = (double)r.w * beta1 * beta1;
+    double em;
+    HalfTerms q = half_terms(wvno, omega * fm::rcp(beta1), d, &em);
+    double e10 = e1 * q.cs + e2 * xmu * q.r_sn;
+    double e20 = e1 * q.sn_over_r * fm::rcp(xmu) + e2 * q.cs;
+    double xnor = fm::absmax(e10, e20);
+    if (xnor < 1.0e-40) xnor = 1.0;
+    if (l == 0) return e10 / xnor;          // IEEE division: exact +-1.0 when saturated
+    double inv = fm::rcp(xnor);
+    e1 = e10 * inv;
+    e2 = e20 * inv;
+  }
+  return e1;
+}
+
+BH_HD double secular_rayleigh_fast(const LayerRow* rows, int stride, int L, double wvno, double omga) {
+  double omega = (omga < 1.0e-4) ? 1.0e-4 : omga;
+  double iomega = fm::rcp(omega);
+  double wvno2 = wvno * wvno;
+  double e0, e1, e2, e3, e4;
+  {
+    LayerRow hs = rows[(L - 1) * stride];
+    double a = (double)hs.y, b = (double)hs.z, rho1 = (double)hs.w;
+    double xka = omega * fm::rcp(a), xkb = omega * fm::rcp(b);
+    double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    double t = b * iomega;
+    double gammk = 2.0 * t * t;
+    double gam = gammk * wvno2;
+    double gamm1 = gam - 1.0;
+    e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
+    e1 = -rho1 * ra;
+    e2 = rho1 * (gamm1 - gammk * ra * rb);
+    e3 = rho1 * rb;
+    e4 = wvno2 - ra * rb;
+  }
+  for (int l = L - 2; l >= 0; --l) {
+    LayerRow r = rows[l * stride];
+    double dpth = (double)r.x, a = (double)r.y, b = (double)r.z, rho = (double)r.w;
+    double t = b * iomega;
+    double gammk = 2.0 * t * t;
+    double gam = gammk * wvno2;
+    double ep, eq;
+    HalfTerms P = half_terms(wvno, omega * fm::rcp(a), dpth, &ep);
+    HalfTerms S = half_terms(wvno, omega * fm::rcp(b), dpth, &eq);
+    double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
+    double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
+    double exa = P.ex + S.ex;
+    double a0 = (exa < 60.0) ? ep * eq : 0.0;
+    double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
+    double xy = x * y, xz = x * z, wy = w * y, wz = w * z;
+    double gamm1 = gam - 1.0;
+    double twgm1 = gam + gamm1;
+    double gmgmk = gam * gammk;
+    double gmgm1 = gam * gamm1;
+    double gm1sq = gamm1 * gamm1;
+    double rho2 = rho * rho;
+    double rinv = fm::rcp(rho);
+    double a0pq = a0 - cpcq;
+    double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
+    double c12 = (wvno2 * cpy - cqx) * rinv;
+    double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * rinv;
+    double c14 = (cpz - wvno2 * cqw) * rinv;
+    double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * (rinv * rinv);
+    double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
+    double c22 = cpcq;
+    double c23 = gammk * cpz - gamm1 * cqw;
+    double c24 = -wz;
+    double c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
+    double c42 = -xy;
+    double c43 = gamm1 * cpy - gammk * cqx;
+    double c51 = -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
+    double c53 = -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
+    double tt = -2.0 * wvno2;
+    double c31 = tt * c53, c32 = tt * c43, c33 = a0 + 2.0 * (cpcq - c11), c34 = tt * c23, c35 = tt * c13;
+    double n0 = e0 * c11 + e1 * c21 + e2 * c31 + e3 * c41 + e4 * c51;
+    double n1 = e0 * c12 + e1 * c22 + e2 * c32 + e3 * c42 + e4 * c41;
+    double n2 = e0 * c13 + e1 * c23 + e2 * c33 + e3 * c43 + e4 * c53;
+    double n3 = e0 * c14 + e1 * c24 + e2 * c34 + e3 * c22 + e4 * c21;
+    double n4 = e0 * c15 + e1 * c14 + e2 * c35 + e3 * c12 + e4 * c11;
+    double t1 = fm::absmax(fm::absmax(fm::absmax(n0, n1), fm::absmax(n2, n3)), n4);
+    if (t1 < 1.0e-40) t1 = 1.0;
+    if (l == 0) return n0 / t1;             // IEEE division: exact +-1.0 when saturated
+    double inv = fm::rcp(t1);
+    e0 = n0 * inv; e1 = n1 * inv; e2 = n2 * inv; e3 = n3 * inv; e4 = n4 * inv;
+  }
+  return e0;
+}
+
+// BH_SECULAR_REFERENCE_ORDER (tests/host_sim only) selects the formulation that
+// follows the Fortran operation by operation, for bit-equality with the oracle.
 BH_HD double secular(int wave /*1 Love, 2 Rayleigh*/, const LayerRow* rows, int stride, int L,
                      double wvno, double omega) {
-  return wave == 1 ? secular_love(rows, stride, L, wvno, omega)
-                   : secular_rayleigh(rows, stride, L, wvno, omega);
+#if defined(BH_SECULAR_REFERENCE_ORDER)
+  return wave == 1 ? secular_love_reforder(rows, stride, L, wvno, omega)
+                   : secular_rayleigh_reforder(rows, stride, L, wvno, omega);
+#else
+  return wave == 1 ? secular_love_fast(rows, stride, L, wvno, omega)
+                   : secular_rayleigh_fast(rows, stride, L, wvno, omega);
+#endif
 }
 
 // ---------------------------------------------------------------------------

@@ -170,6 +170,11 @@ int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a,
              const double* qp, const double* qs, double* fz, double* fr,
              double* rf);
 
+/* Diagnostics: evaluates the engine's straight-line fp64 elementary functions on
+ * the device for n HOST values x; out[7][n] = exp(-|x|), sin x, cos x, 1/x,
+ * sqrt|x|, 1/sqrt|x|, 1.0/x (faithful division).  Used by the accuracy tests. */
+int bh_debug_math(int n, const double* x, double* out);
+
 #ifdef __cplusplus
 }
 #endif

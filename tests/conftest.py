@@ -23,18 +23,28 @@ def oracle():
     return joint_oracle
 
 
-@pytest.fixture(scope="session")
-def host_sim():
-    """Host lock-step simulation of the device cores (tests/host_sim)."""
+def _build_host_sim(name, defines=()):
     import ctypes
     src = os.path.join(ROOT, "tests", "host_sim", "core_sim.cpp")
-    so = os.path.join(ROOT, "tests", "host_sim", "libcore_sim.so")
+    so = os.path.join(ROOT, "tests", "host_sim", name)
     deps = [src] + [os.path.join(ROOT, "bayhunter_b200", "csrc", f)
-                    for f in ("bh_common.cuh", "swd_core.cuh", "rf_core.cuh")]
+                    for f in ("bh_common.cuh", "bh_math.cuh", "swd_core.cuh", "rf_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                        "-o", so, src, "-lm"], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] +
+                       ["-D" + d for d in defines] + ["-o", so, src, "-lm"], check=True)
     return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="session")
+def host_sim():
+    """Host lock-step simulation of the device cores, device formulation of the secular functions."""
+    return _build_host_sim("libcore_sim.so")
+
+
+@pytest.fixture(scope="session")
+def host_sim_reforder():
+    """Same, with the secular functions in the Fortran's operation order (bit-equal to the oracle)."""
+    return _build_host_sim("libcore_sim_ref.so", ("BH_SECULAR_REFERENCE_ORDER",))
 
 
 @pytest.fixture(scope="session")

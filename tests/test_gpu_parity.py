@@ -288,3 +288,32 @@ def test_full_size_properties():
     assert status.mean() > 0.5
     ok = status == 1
     assert np.isfinite(logL[ok]).all() and np.all(logL[~ok] == -1e15)
+
+
+def test_device_elementary_functions_accuracy():
+    """bh_math.cuh (straight-line exp / sincos / rcp / sqrt / rsqrt / div) vs libm, in ulps."""
+    import ctypes
+    from bayhunter_b200 import _lib
+    lib = _lib.require_device()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 0, 20000), rng.uniform(-400, 400, 40000),
+                        rng.uniform(-1e-3, 1e-3, 5000), np.array([1e-300, 1.0, -1.0, 0.5, 16.0, 60.0, 699.9]),
+                        np.pi / 2 * np.arange(1, 2000) * (1 + 1e-16)])
+    x = np.ascontiguousarray(x[x != 0.0])
+    n = x.size
+    out = np.zeros((7, n))
+    _lib.check(lib.bh_debug_math(n, x.ctypes.data_as(_lib.c_double_p), out.ctypes.data_as(_lib.c_double_p)))
+
+    def ulps(a, b):
+        return np.abs(a - b) / np.spacing(np.abs(b))
+    m = np.abs(x) <= 700
+    assert ulps(out[0][m], np.exp(-np.abs(x[m]))).max() <= 2.0
+    # sin/cos: absolute error bounded by ~1 ulp of 1 plus relative 2 ulp away from zeros
+    assert np.abs(out[1] - np.sin(x)).max() <= 4e-16 and np.abs(out[2] - np.cos(x)).max() <= 4e-16
+    big = np.abs(np.sin(x)) > 1e-3
+    assert ulps(out[1][big], np.sin(x)[big]).max() <= 3.0
+    norm = np.abs(x) > 1e-290
+    assert ulps(out[3][norm], 1.0 / x[norm]).max() <= 1.0
+    assert ulps(out[4][norm], np.sqrt(np.abs(x[norm]))).max() <= 1.0
+    assert ulps(out[5][norm], 1.0 / np.sqrt(np.abs(x[norm]))).max() <= 2.0
+    assert ulps(out[6][norm], 1.0 / x[norm]).max() <= 1.0

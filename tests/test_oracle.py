@@ -1,0 +1,120 @@
+"""CPU tests of the oracle (oracle/): pinned to the reference's golden fixtures
+(tutorial/observed/st3_*.dat, copied to tests/golden/) and, where the compiled
+reference rfmini is available (oracle/_ref), to the reference itself."""
+import numpy as np
+import pytest
+
+ST3_H = np.array([5., 23., 8., 0.])
+ST3_VS = np.array([2.7, 3.6, 3.8, 4.4])
+ST3_VP = ST3_VS * 1.73
+ST3_RHO = ST3_VP * 0.32 + 0.77
+
+
+@pytest.mark.parametrize("ref", ["rdispph", "rdispgr", "ldispph", "ldispgr"])
+def test_surf96_restatement_reproduces_golden_dispersion(ref, oracle, golden_dir):
+    d = np.loadtxt("%s/st3_%s.dat" % (golden_dir, ref))
+    x, y = oracle.surfdisp(ST3_H, ST3_VP, ST3_VS, ST3_RHO, ref, d[:, 0])
+    assert np.array_equal(x, d[:, 0])
+    # files hold 4 decimals: |err| <= 5e-5 (+ float slack)
+    assert np.abs(y - d[:, 1]).max() <= 5.0e-5 + 1e-9
+
+
+def test_surf96_secular_evaluation_counts(oracle):
+    """SURVEY App. E probe: 643 secular evaluations for the st3 Rayleigh phase curve."""
+    cnt = [0, 0]
+    oracle.surfdisp(ST3_H, ST3_VP, ST3_VS, ST3_RHO, "rdispph", np.linspace(1, 41, 21), count=cnt)
+    assert cnt == [401, 242]
+
+
+def test_surf96_failure_flag_and_outputs_are_fp32(oracle):
+    x, y = oracle.surfdisp(np.array([0.]), np.array([6.0]), np.array([3.5]), np.array([2.7]),
+                           "ldispph", np.linspace(1, 40, 20))
+    assert not isinstance(x, np.ndarray) and np.isnan(y)       # Love on a half-space: err = 1
+    x, y = oracle.surfdisp(ST3_H, ST3_VP, ST3_VS, ST3_RHO, "rdispph", np.linspace(1, 40, 20))
+    assert np.array_equal(y, y.astype(np.float32).astype(np.float64))   # cg = sngl(c)
+
+
+def test_surf96_more_than_60_periods_interpolates(oracle):
+    p = np.linspace(2, 50, 75)
+    x, y = oracle.surfdisp(ST3_H, ST3_VP, ST3_VS, ST3_RHO, "rdispph", p)
+    assert x.size == 75 and np.all(np.diff(y) > -1e-3)
+
+
+@pytest.mark.parametrize("ref", ["prf", "srf"])
+def test_rf_oracle_golden_and_reference(ref, oracle, golden_dir):
+    d = np.loadtxt("%s/st3_%s.dat" % (golden_dir, ref))
+    w = "SV" if ref == "srf" else "P"
+    t, y = oracle.recfunc(ST3_H, ST3_VP, ST3_VS, ST3_RHO, d[:, 0], wtype=w, use_reference=False)
+    assert np.allclose(t, d[:, 0], atol=1e-9)
+    assert np.abs(y - d[:, 1]).max() <= 1.0e-4            # fixtures pin ~1e-4 only
+    if oracle.ref_rfmini() is not None:                     # the reference's own C++
+        _, yr = oracle.recfunc(ST3_H, ST3_VP, ST3_VS, ST3_RHO, d[:, 0], wtype=w, use_reference=True)
+        assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
+
+
+def test_rf_restatement_matches_compiled_reference_on_random_models(oracle):
+    if oracle.ref_rfmini() is None:
+        pytest.skip("oracle/_ref/librfmini_ref.so not built (no /root/reference here)")
+    from bayhunter_b200 import synthetic
+    rng = np.random.default_rng(3)
+    for it in range(60):
+        k = int(rng.integers(2, 32))
+        h, vs = synthetic.draw_model(rng, k)
+        vp = vs * rng.uniform(1.4, 2.1)
+        rho = vp * 0.32 + 0.77
+        x = -5 + 0.1 * np.arange(512) if it % 2 else -5 + 0.2 * np.arange(201)
+        kw = dict(gauss=float(rng.uniform(0.8, 2.5)), p=float(rng.uniform(4.5, 8.0)))
+        for w in ("P", "SV"):
+            _, a = oracle.recfunc(h, vp, vs, rho, x, wtype=w, use_reference=False, **kw)
+            _, b = oracle.recfunc(h, vp, vs, rho, x, wtype=w, use_reference=True, **kw)
+            assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+
+
+def test_golden_random_vectors(oracle, golden_dir):
+    """Vectors generated HERE from the compiled reference rfmini + the reference's own
+    Targets.py (tests/golden/make_golden.py); they travel to the GPU box."""
+    import os
+    path = os.path.join(golden_dir, "golden_random.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden_random.npz not generated")
+    g = np.load(path)
+    for i in range(g["rf_rows"].shape[0]):
+        n = int(g["rf_nlay"][i])
+        vs = g["rf_rows"][i, :n, 0]; vp = vs * g["rf_rows"][i, :n, 1]; h = g["rf_rows"][i, :n, 3]
+        _, y = oracle.recfunc(h, vp, vs, vp * 0.32 + 0.77, g["rf_x"], wtype="P", use_reference=False)
+        assert np.abs(y - g["rf_y"][i]).max() <= 1e-12 * np.abs(g["rf_y"][i]).max()
+
+
+def test_likelihood_closed_forms_match_dense(oracle):
+    """The device kernels use closed forms of d^T C^-1 d; check them against the dense
+    matrices of the literal restatement (Targets.py:105-148)."""
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 21, 201):
+        d = rng.normal(0, 0.05, n)
+        for corr in (0.0, 0.35, 0.9):
+            sigma = 0.013
+            if n > 1:
+                c_inv, logdet = oracle.cov_exp(corr, sigma, n)
+                s0 = np.sum(d * d); s1 = np.sum(d[1:-1] ** 2); s2 = np.sum(d[:-1] * d[1:])
+                phi = (s0 + corr ** 2 * s1 - 2 * corr * s2) / (sigma ** 2 * (1 - corr ** 2))
+                assert np.isclose(d.dot(c_inv).dot(d), phi, rtol=1e-12)
+        yerr = rng.uniform(0.01, 0.05, n)
+        c_inv, logdet = oracle.cov_nocorr_scalederr(0.02, n, yerr)
+        assert np.isclose(d.dot(c_inv).dot(d), np.sum(d * d / (yerr / yerr.min())) / 0.02 ** 2, rtol=1e-12)
+
+
+def test_likelihood_against_synthobs_formulas(oracle):
+    """Second, independent statement of the same maths in the reference:
+    SynthObs.compute_explike (src/SynthObs.py:193-222) -- white and exp laws."""
+    rng = np.random.default_rng(1)
+    n, sigma, corr = 50, 0.02, 0.6
+    yobs = rng.normal(0, 1, n); ymod = yobs + rng.normal(0, sigma, n)
+    t = oracle.OracleTarget("prf", np.arange(n) * 0.2, yobs, cov="exp")
+    c_inv, logdet = t.covariance(corr, sigma)
+    d = ymod - yobs
+    logL = -0.5 * (n * np.log(2 * np.pi) + logdet) - d.dot(c_inv).dot(d) / 2
+    # explicit covariance matrix C_ij = sigma^2 corr^|i-j|, dense inverse and determinant
+    C = sigma ** 2 * corr ** np.abs(np.subtract.outer(np.arange(n), np.arange(n)))
+    sign, ld = np.linalg.slogdet(C)
+    logL2 = -0.5 * (n * np.log(2 * np.pi) + ld) - d.dot(np.linalg.inv(C)).dot(d) / 2
+    assert np.isclose(logL, logL2, rtol=1e-9)

@@ -47,6 +47,9 @@ def run(cfg, B, settings, reps=3):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "one":      # one setting, for ncu: tools/quick_bench.py one <cfg> <B> <spw> <spec> <conc>
+        cfg, B, spw, spec, conc = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+        run(cfg, B, [dict(swd_searches_per_warp=spw, swd_max_spec=spec, concurrent=conc)], reps=2)
     if which in ("all", "joint5"):
         run("joint5", 8192, [dict(swd_searches_per_warp=s, swd_max_spec=m, concurrent=c)
                              for (s, m, c) in ((32, 1, 0), (32, 8, 0), (16, 8, 0), (8, 8, 0), (4, 8, 0),
