@@ -68,7 +68,9 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    """In-tree shared object; BH_B200_LIB selects another build of the SAME ABI
+    (developer A/B runs of kernel variants, tools/quick_bench.py)."""
+    return os.environ.get("BH_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):
@@ -79,7 +81,7 @@ def load(build_if_missing=True):
             return _lib
         path = library_path()
         if not os.path.exists(path):
-            if not build_if_missing:
+            if not build_if_missing or path != _build.LIB:
                 raise BayHunterB200Error(BH_ERR_NO_DEVICE, "%s is missing; run __graft_entry__.build()" % path)
             _build.build()
         lib = ctypes.CDLL(path)

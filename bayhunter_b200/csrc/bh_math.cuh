@@ -11,12 +11,51 @@
 // where exactness matters (the final +-1.0 saturation of the secular value)
 // keeps an IEEE division in swd_core.cuh.
 //
+// All polynomial / reduction constants live in ONE __constant__ table so that
+// every DFMA takes its coefficient straight from the constant bank
+// (DFMA R, R, R, c[3][off]).  Written as literals, ptxas re-materialises each
+// 64-bit constant with two UMOV/IMAD.MOV per use, which was ~1/3 of all
+// instructions issued by the dispersion kernel (profiles/r01_swd_v1_summary.txt).
+//
 // Host builds (tests/host_sim) map everything to libm.
 #pragma once
 #include "bh_common.cuh"
 
 namespace bh {
 namespace fm {
+
+#if defined(__CUDACC__)
+enum {
+  K_MAGIC = 0,      // 1.5 * 2^52
+  K_LOG2E, K_LN2_HI, K_LN2_LO,
+  K_E13, K_E12, K_E11, K_E10, K_E9, K_E8, K_E7, K_E6, K_E5, K_E4, K_E3,
+  K_TWO_OVER_PI, K_PIO2_1, K_PIO2_2, K_PIO2_3,
+  K_S6, K_S5, K_S4, K_S3, K_S2, K_S1,
+  K_C6, K_C5, K_C4, K_C3, K_C2, K_C1,
+  K_COUNT
+};
+static __constant__ double kTab[K_COUNT] = {
+    6755399441055744.0,
+    1.4426950408889634, 0.6931471805599453, 2.3190468138462996e-17,
+    1.6059043836821613e-10,   // 1/13!
+    2.08767569878681e-09,     // 1/12!
+    2.505210838544172e-08,    // 1/11!
+    2.755731922398589e-07,    // 1/10!
+    2.7557319223985893e-06,   // 1/9!
+    2.48015873015873e-05,     // 1/8!
+    1.984126984126984e-04,    // 1/7!
+    1.388888888888889e-03,    // 1/6!
+    8.333333333333333e-03,    // 1/5!
+    4.1666666666666664e-02,   // 1/4!
+    1.6666666666666666e-01,   // 1/3!
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+};
+#define BH_K(i) (::bh::fm::kTab[::bh::fm::i])
+#endif
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ double hi_lo(int hi, int lo) { return __hiloint2double(hi, lo); }
@@ -70,26 +109,26 @@ BH_HD void sqrt_rsqrt(double x, double* s, double* rs) {
 #endif
 }
 
-// exp(x) for x in [-700, 0.7]
+// exp(x) for x in [-700, 0.7].  Out-of-range arguments give garbage (never a
+// trap); the callers select the result away in that case.
 BH_HD double exp_small(double x) {
 #if defined(__CUDA_ARCH__)
-  const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52
-  double t = fma(x, 1.4426950408889634, MAGIC);          // round(x * log2 e) in the low word
+  double t = fma(x, BH_K(K_LOG2E), BH_K(K_MAGIC));       // round(x * log2 e) in the low word
   int n = __double2loint(t);
-  double fn = t - MAGIC;
-  double r = fma(-fn, 0.6931471805599453, x);
-  r = fma(-fn, 2.3190468138462996e-17, r);                // |r| <= 0.3466
-  double p = 1.6059043836821613e-10;                      // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);                    // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);                   // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);                   // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);                  // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);                    // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);                   // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);                   // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);                   // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);                  // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);                  // 1/3!
+  double fn = t - BH_K(K_MAGIC);
+  double r = fma(-fn, BH_K(K_LN2_HI), x);
+  r = fma(-fn, BH_K(K_LN2_LO), r);                       // |r| <= 0.3466
+  double p = BH_K(K_E13);
+  p = fma(p, r, BH_K(K_E12));
+  p = fma(p, r, BH_K(K_E11));
+  p = fma(p, r, BH_K(K_E10));
+  p = fma(p, r, BH_K(K_E9));
+  p = fma(p, r, BH_K(K_E8));
+  p = fma(p, r, BH_K(K_E7));
+  p = fma(p, r, BH_K(K_E6));
+  p = fma(p, r, BH_K(K_E5));
+  p = fma(p, r, BH_K(K_E4));
+  p = fma(p, r, BH_K(K_E3));
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
@@ -103,34 +142,37 @@ BH_HD double exp_small(double x) {
 // + the classic minimax kernels on [-pi/4, pi/4]
 BH_HD void sincos_cw(double x, double* sn, double* cs) {
 #if defined(__CUDA_ARCH__)
-  const double MAGIC = 6755399441055744.0;
-  double t = fma(x, 0.6366197723675814, MAGIC);
+  double t = fma(x, BH_K(K_TWO_OVER_PI), BH_K(K_MAGIC));
   int q = __double2loint(t);
-  double fn = t - MAGIC;
-  double r = fma(-fn, 1.5707963267948966, x);
-  r = fma(-fn, 6.123233995736766e-17, r);
-  r = fma(-fn, -1.4973849048591698e-33, r);
+  double fn = t - BH_K(K_MAGIC);
+  double r = fma(-fn, BH_K(K_PIO2_1), x);
+  r = fma(-fn, BH_K(K_PIO2_2), r);
+  r = fma(-fn, BH_K(K_PIO2_3), r);
   double z = r * r;
-  double ps = 1.58969099521155010221e-10;
-  ps = fma(ps, z, -2.50507602534068634195e-08);
-  ps = fma(ps, z, 2.75573137070700676789e-06);
-  ps = fma(ps, z, -1.98412698298579493134e-04);
-  ps = fma(ps, z, 8.33333333332248946124e-03);
-  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double ps = BH_K(K_S6);
+  ps = fma(ps, z, BH_K(K_S5));
+  ps = fma(ps, z, BH_K(K_S4));
+  ps = fma(ps, z, BH_K(K_S3));
+  ps = fma(ps, z, BH_K(K_S2));
+  ps = fma(ps, z, BH_K(K_S1));
   double s = fma(r * z, ps, r);
-  double pc = -1.13596475577881948265e-11;
-  pc = fma(pc, z, 2.08757232129817482790e-09);
-  pc = fma(pc, z, -2.75573143513906633035e-07);
-  pc = fma(pc, z, 2.48015872894767294178e-05);
-  pc = fma(pc, z, -1.38888888888741095749e-03);
-  pc = fma(pc, z, 4.16666666666666019037e-02);
+  double pc = BH_K(K_C6);
+  pc = fma(pc, z, BH_K(K_C5));
+  pc = fma(pc, z, BH_K(K_C4));
+  pc = fma(pc, z, BH_K(K_C3));
+  pc = fma(pc, z, BH_K(K_C2));
+  pc = fma(pc, z, BH_K(K_C1));
   double hz = 0.5 * z;
   double w = 1.0 - hz;
   double c = w + (((1.0 - w) - hz) + z * z * pc);
+  // quadrant: swap on bit 0, negate sin on bit 1, cos on bit 0 ^ bit 1 -- the
+  // sign flips are integer XORs on the high words
   double a = (q & 1) ? c : s;
   double b = (q & 1) ? s : c;
-  *sn = (q & 2) ? -a : a;
-  *cs = ((q + 1) & 2) ? -b : b;
+  int sa = (q & 2) << 30;
+  int sb = ((q + 1) & 2) << 30;
+  *sn = hi_lo(__double2hiint(a) ^ sa, __double2loint(a));
+  *cs = hi_lo(__double2hiint(b) ^ sb, __double2loint(b));
 #else
   *sn = sin(x);
   *cs = cos(x);
@@ -141,6 +183,38 @@ BH_HD void sincos_cw(double x, double* sn, double* cs) {
 BH_HD double absmax(double a, double b) {
   double x = fabs(a), y = fabs(b);
   return x > y ? x : y;
+}
+
+// 2^-k with k = the binary exponent of max(|v0..v4|): an exact power-of-two
+// scale that brings the largest component into [1, 2).  Integer compares on the
+// high words only; zero / denormal maxima give 2^1023 (harmless: 0 stays 0).
+BH_HD double pow2_rescale5(double v0, double v1, double v2, double v3, double v4) {
+#if defined(__CUDA_ARCH__)
+  int m0 = __double2hiint(v0) & 0x7fffffff, m1 = __double2hiint(v1) & 0x7fffffff;
+  int m2 = __double2hiint(v2) & 0x7fffffff, m3 = __double2hiint(v3) & 0x7fffffff;
+  int m4 = __double2hiint(v4) & 0x7fffffff;
+  int m = max(max(max(m0, m1), max(m2, m3)), m4);
+  return hi_lo(0x7fe00000 - (m & 0x7ff00000), 0);
+#else
+  double t = absmax(absmax(absmax(v0, v1), absmax(v2, v3)), v4);
+  if (!(t > 0.0)) return 1.0;
+  int e;
+  frexp(t, &e);             // t = f * 2^e, f in [0.5, 1)
+  return ldexp(1.0, 1 - e);
+#endif
+}
+BH_HD double pow2_rescale2(double v0, double v1) {
+#if defined(__CUDA_ARCH__)
+  int m0 = __double2hiint(v0) & 0x7fffffff, m1 = __double2hiint(v1) & 0x7fffffff;
+  int m = max(m0, m1);
+  return hi_lo(0x7fe00000 - (m & 0x7ff00000), 0);
+#else
+  double t = absmax(v0, v1);
+  if (!(t > 0.0)) return 1.0;
+  int e;
+  frexp(t, &e);
+  return ldexp(1.0, 1 - e);
+#endif
 }
 
 }  // namespace fm

@@ -66,6 +66,7 @@ struct bh_engine {
   PrepOut prep{};
   cd* spec = nullptr;
   double* curves = nullptr;
+  double* roots = nullptr;
   int curve_stride = 0;
   int curve_off[kMaxTargets] = {0};
   double* rfsynth = nullptr;
@@ -79,7 +80,8 @@ struct bh_engine {
   cudaStream_t s_own = nullptr, s_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // tunables
-  int searches_per_warp = 0;  // 0 = auto
+  int searches_per_warp = 0;  // phase-velocity curves; 0 = auto
+  int group_spw = 0;          // group-velocity curves; 0 = half of the above
   int max_spec = 8;
   int concurrent = 1;
   // optional per-kernel timing (bh_engine_set "profile"): event pairs around
@@ -236,6 +238,7 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
   if (rc == BH_OK && nrf) rc = scratch(e, &e->prep.rf_mc, B * 16);
   if (rc == BH_OK && nrf) rc = scratch(e, &e->spec, B * e->max_nfreq);
   if (rc == BH_OK) rc = scratch(e, &e->curves, B * e->curve_stride);
+  if (rc == BH_OK) rc = scratch(e, &e->roots, 2 * B * e->curve_stride);
   if (rc == BH_OK) rc = scratch(e, &e->rfsynth, B * (size_t)off);
   if (rc == BH_OK) rc = scratch(e, &e->tstatus, B * kMaxTargets);
   if (rc == BH_OK) rc = scratch(e, &e->counters, 2);
@@ -269,6 +272,9 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   if (!strcmp(key, "swd_searches_per_warp")) {
     if (value < 0 || value > 32 || (value & (value - 1))) return set_err(BH_ERR_ARG, "searches_per_warp must be 0 (auto) or a power of two <= 32");
     e->searches_per_warp = value;
+  } else if (!strcmp(key, "swd_group_searches_per_warp")) {
+    if (value < 0 || value > 32 || (value & (value - 1))) return set_err(BH_ERR_ARG, "group searches_per_warp must be 0 (auto) or a power of two <= 32");
+    e->group_spw = value;
   } else if (!strcmp(key, "swd_max_spec")) {
     if (value < 1 || value > 32) return set_err(BH_ERR_ARG, "swd_max_spec must be 1..32");
     e->max_spec = value;
@@ -297,16 +303,20 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
 
   SwdLaunch sw{};
   int first_rf = -1;
-  for (int t = 0; t < ts.ntargets; ++t) {
-    const TargetDev& d = ts.t[t];
-    if (is_swd(d.ref)) {
+  // curves in order of decreasing serial work so that the longest chains start
+  // first: Rayleigh group, Rayleigh phase, Love group, Love phase
+  for (int pass = 0; pass < 4; ++pass) {
+    const int want_wave = pass < 2 ? 2 : 1, want_igr = (pass & 1) ? 0 : 1;
+    for (int t = 0; t < ts.ntargets; ++t) {
+      const TargetDev& d = ts.t[t];
+      if (!is_swd(d.ref) || d.wave != want_wave || d.igr != want_igr) continue;
       int c = sw.ncurves++;
       sw.target_id[c] = t; sw.wave[c] = d.wave; sw.igr[c] = d.igr; sw.kmax[c] = d.kmax;
       sw.periods[c] = d.periods; sw.curve_off[c] = e->curve_off[t]; sw.synth_off[c] = d.synth_off;
-    } else if (first_rf < 0) {
-      first_rf = t;
     }
   }
+  for (int t = 0; t < ts.ntargets; ++t)
+    if (is_rf(ts.t[t].ref)) { first_rf = t; break; }
   const bool have_rf = first_rf >= 0;
   PrepOut prep = e->prep;
   prep.swd_stride = odd_stride(lmax);   // rows of this batch; buffer is sized for max_layers
@@ -324,16 +334,24 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     { KTimer kt(e, BH_K_PREP_SWD, st);
       launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st); }
     sw.rows = prep.swd_rows; sw.row_stride = prep.swd_stride; sw.nlay = nlay; sw.B = B;
-    sw.curves = e->curves; sw.curve_stride = e->curve_stride;
+    sw.curves = e->curves; sw.roots = e->roots; sw.curve_stride = e->curve_stride;
     sw.tstatus = e->tstatus; sw.counters = e->counters;
-    int S = e->searches_per_warp;
+    sw.lcap = lmax;
+    // searches per warp: phase curves S, group curves S_g (two roots per period ->
+    // about twice the serial chain -> more lanes per search for bracket speculation)
+    int S = e->searches_per_warp, Sg = e->group_spw;
     if (S == 0) {
-      // enough warps to give every SM sub-partition a few (148 SMs x 4 x ~3.5)
+      // enough warps to give every SM sub-partition a few (148 SMs x 4 x ~3)
       const long long nsearch = (long long)B * sw.ncurves;
       S = 32;
-      while (S > 1 && nsearch / S < 2048) S >>= 1;
+      while (S > 1 && nsearch / S < 1776) S >>= 1;
     }
-    sw.searches_per_warp = S;
+    if (Sg == 0) Sg = S > 1 ? S / 2 : 1;
+    if (Sg > 16) Sg = 16;                 // two chains (lanes) per group search
+    // keep one warp's records within ~16 KB of shared memory
+    while (S > 1 && swd_smem_bytes(lmax, S) > 16 * 1024) S >>= 1;
+    while (Sg > 1 && swd_smem_bytes(lmax, Sg) > 16 * 1024) Sg >>= 1;
+    for (int c = 0; c < sw.ncurves; ++c) sw.spw[c] = sw.igr[c] ? Sg : S;
     sw.max_spec = e->max_spec;
     { KTimer kt(e, BH_K_SWD, st); launch_swd(sw, st); }
   }
@@ -430,6 +448,7 @@ struct Shim {
   LayerRow* rows = nullptr;
   double* periods = nullptr;
   double* curve = nullptr;
+  double* roots = nullptr;
   int* nlay = nullptr;
   int* tstatus = nullptr;
   double* model6 = nullptr;      // z, vp, vs, rho, qp, qs  (6 x 100)
@@ -450,6 +469,7 @@ int shim_init() {
   BH_CUDA(cudaMalloc((void**)&g_shim.rows, sizeof(LayerRow) * 101));
   BH_CUDA(cudaMalloc((void**)&g_shim.periods, sizeof(double) * BH_MAX_PERIODS));
   BH_CUDA(cudaMalloc((void**)&g_shim.curve, sizeof(double) * BH_MAX_PERIODS));
+  BH_CUDA(cudaMalloc((void**)&g_shim.roots, sizeof(double) * 2 * BH_MAX_PERIODS));
   BH_CUDA(cudaMalloc((void**)&g_shim.nlay, sizeof(int)));
   BH_CUDA(cudaMalloc((void**)&g_shim.tstatus, sizeof(int) * kMaxTargets));
   BH_CUDA(cudaMalloc((void**)&g_shim.model6, sizeof(double) * 6 * BH_MAX_LAYERS));
@@ -484,8 +504,8 @@ int bh_surfdisp96(const float* thkm, const float* vpm, const float* vsm, const f
   SwdLaunch sw{};
   sw.rows = s.rows; sw.row_stride = odd_stride(nlayer); sw.nlay = s.nlay; sw.B = 1; sw.ncurves = 1;
   sw.target_id[0] = 0; sw.wave[0] = iwave; sw.igr[0] = igr > 0 ? 1 : 0; sw.kmax[0] = kmax;
-  sw.periods[0] = s.periods; sw.curves = s.curve; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
-  sw.tstatus = s.tstatus; sw.counters = nullptr; sw.searches_per_warp = 1; sw.max_spec = 32;
+  sw.periods[0] = s.periods; sw.curves = s.curve; sw.roots = s.roots; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
+  sw.tstatus = s.tstatus; sw.counters = nullptr; sw.spw[0] = 1; sw.lcap = nlayer; sw.max_spec = 32;
   launch_swd(sw, s.st);
   int ok = 0;
   std::vector<double> out(kmax);

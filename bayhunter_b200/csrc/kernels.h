@@ -56,8 +56,9 @@ void launch_prepare_rf_explicit(const double* z, const double* vp, const double*
 
 // ---- surface-wave dispersion ----------------------------------------------
 struct SwdLaunch {
-  const LayerRow* rows;
+  const LayerRow* rows;         // [B][row_stride] REAL*4 rows (d, vp, vs, rho)
   int row_stride;
+  int lcap;                     // layer capacity of the shared-memory records (>= max nlay)
   const int* nlay;
   int B;
   int ncurves;
@@ -65,14 +66,17 @@ struct SwdLaunch {
   int wave[kMaxTargets], igr[kMaxTargets], kmax[kMaxTargets], synth_off[kMaxTargets];
   const double* periods[kMaxTargets];
   double* curves;               // [B][curve_stride] searched velocities (kmax per curve)
+  double* roots;                // [B][2*curve_stride] scratch: first / second roots of every period
   int curve_stride;
   int curve_off[kMaxTargets];
   int* tstatus;                 // [B][kMaxTargets] 1 ok / 0 failed
   unsigned long long* counters; // [2] consumed / evaluated secular values
-  int searches_per_warp;        // 1..32
+  int spw[kMaxTargets];         // searches per warp of each curve, 1..32
+  int warp_begin[kMaxTargets + 1];  // filled by launch_swd: first warp (= CTA) of each curve
   int max_spec;                 // speculative bracket candidates per search per round
 };
-void launch_swd(const SwdLaunch& p, cudaStream_t st);
+void launch_swd(SwdLaunch& p, cudaStream_t st);
+size_t swd_smem_bytes(int lcap, int S);
 
 // ---- receiver function ----------------------------------------------------
 struct RfLaunch {

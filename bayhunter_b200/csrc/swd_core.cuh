@@ -200,84 +200,196 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
 
 // ---------------------------------------------------------------------------
 // Device formulation of the same two functions: identical algebra, but
-//  * branch-free per layer (the oscillatory / evanescent / grazing cases are
-//    selects; a warp mixing them paid for both sides anyway) so that the P and
-//    S halves and the matrix algebra of a layer form one long basic block with
-//    instruction-level parallelism for the fp64 pipe,
+//  * per-layer constants that do not depend on the trial phase velocity
+//    (1/vp, 1/vs, 1/rho, 2 vs^2, rho vs^2 ...) are derived ONCE per search into
+//    fp64 "records" (swd_make_rec) that the kernel keeps in shared memory,
+//    field-major so that 32 lanes reading the same field of 32 different
+//    models hit 32 different banks,
+//  * branch-free per layer (the oscillatory / evanescent cases are selects; a
+//    warp mixing them paid for both sides anyway) so that the P and S halves
+//    and the matrix algebra of a layer form one long basic block with
+//    instruction-level parallelism for the fp64 pipe; the grazing case
+//    k == omega/v is folded into the oscillatory one by flooring the radicand,
 //  * exp(-2p) = exp(-p)^2 and exp(-(p+q)) = exp(-p) exp(-q): two exponentials
 //    per layer instead of three,
 //  * reciprocals and rsqrt seeds instead of IEEE divisions / square roots
-//    (bh_math.cuh), except the LAST normalisation, whose IEEE division keeps a
-//    saturated secular value at exactly +-1.0 like the reference (nevill's
-//    sign/ratio tests sit on that tie, surfdisp96.f:619,628).
+//    (bh_math.cuh),
+//  * the per-layer renormalisation of the propagated vector multiplies by an
+//    exact power of two (integer compare of the exponent fields) instead of
+//    dividing by the largest component: the secular value is invariant under
+//    that scale, and the serial vector chain loses its longest-latency link.
+//    Only the LAST normalisation is the reference's: its IEEE division keeps a
+//    saturated secular value at exactly +-1.0 (nevill's sign/ratio tests sit
+//    on that tie, surfdisp96.f:619,628).
 // ---------------------------------------------------------------------------
-struct HalfTerms { double cs, sn_over_r, r_sn, ex; };   // cos-like, sin/r, +-r*sin, exponent
+#ifndef BH_SWD_PAIR
+#define BH_SWD_PAIR 0
+#endif
+constexpr int SWD_REC_FIELDS = 6;
+// Rayleigh record fields
+enum { RR_D = 0, RR_IA = 1, RR_IB = 2, RR_RHO = 3, RR_IRHO = 4, RR_TB2 = 5 };
+// Love record fields (half-space row: LR_D holds rho)
+enum { LR_D = 0, LR_IB = 1, LR_MU = 2, LR_IMU = 3 };
+
+// out[f * fs], f < SWD_REC_FIELDS
+BH_HD void swd_make_rec(int wave, const LayerRow& r, bool halfspace, double* out, int fs) {
+  double d = (double)r.x, a = (double)r.y, b = (double)r.z, rho = (double)r.w;
+  if (wave == 1) {
+    double mu = rho * b * b;
+    out[LR_D * fs] = halfspace ? rho : d;
+    out[LR_IB * fs] = fm::rcp(b);
+    out[LR_MU * fs] = mu;
+    out[LR_IMU * fs] = fm::rcp(mu);
+    out[4 * fs] = 0.0;
+    out[5 * fs] = 0.0;
+  } else {
+    out[RR_D * fs] = d;
+    out[RR_IA * fs] = fm::rcp(a);
+    out[RR_IB * fs] = fm::rcp(b);
+    out[RR_RHO * fs] = rho;
+    out[RR_IRHO * fs] = fm::rcp(rho);
+    out[RR_TB2 * fs] = 2.0 * b * b;
+  }
+}
+
+struct HalfTerms { double cs, sn_over_r, r_sn, ex, em; };   // cos-like, sin/r, +-r*sin, exponent, exp(-ex)
 
 // `var` for one wave type of one layer (surfdisp96.f:929-968): k = wvno, xk = omega/v,
-// s = (k+xk)|k-xk|, d = thickness.  Returns cosp, w = sinp/ra, x = -+ra*sinp and the
-// evanescent exponent pex (0 unless k > xk); *e_out = exp(-p) (1 if not evanescent).
-BH_HD HalfTerms half_terms(double k, double xk, double d, double* e_out) {
+// s = (k+xk)|k-xk|, d = thickness.  Returns cosp, w = sinp/ra, x = -+ra*sinp, the
+// evanescent exponent pex (0 unless k > xk) and exp(-pex).
+BH_HD HalfTerms half_terms(double k, double xk, double d) {
   double s = (k + xk) * fabs(k - xk);
+  // grazing (k == xk, reference: cosp = 1, w = d, x = 0): a floored radicand on
+  // the oscillatory side gives cos(1e-100 d) = 1, sin(p)/r = d, r sin(p) = 1e-200 d
+  s = (s < 1.0e-200) ? 1.0e-200 : s;
+  const bool osc = k <= xk;
   double r, ir;
   fm::sqrt_rsqrt(s, &r, &ir);
   double p = r * d;
-  double em = fm::exp_small(fmax(-p, -700.0));
+  double pm = osc ? 0.0 : p;
+  double em = fm::exp_small(-pm);
   double sn, cs;
   fm::sincos_cw(p, &sn, &cs);
-  const bool osc = k < xk, graze = (k == xk);
-  double fac = (p < 16.0) ? em * em : 0.0;
+  double fac = (pm < 16.0) ? em * em : 0.0;
+  double ch = fma(fac, 0.5, 0.5), sh = fma(fac, -0.5, 0.5);
   HalfTerms h;
-  double sh = osc ? sn : (1.0 - fac) * 0.5;
-  h.cs = osc ? cs : (1.0 + fac) * 0.5;
-  h.sn_over_r = sh * ir;
-  double rs = r * sh;
+  h.cs = osc ? cs : ch;
+  double sx = osc ? sn : sh;
+  h.sn_over_r = sx * ir;
+  double rs = r * sx;
   h.r_sn = osc ? -rs : rs;
-  h.ex = osc ? 0.0 : p;
-  *e_out = osc ? 1.0 : em;
-  if (graze) { h.cs = 1.0; h.sn_over_r = d; h.r_sn = 0.0; h.ex = 0.0; *e_out = 1.0; }
+  h.ex = pm;
+  h.em = em;
   return h;
 }
 
-BH_HD double secular_love_fast(const LayerRow* rows, int stride, int L, double wvno, double omega) {
-  LayerRow hs = rows[(L - 1) * stride];
-  double beta1 = (double)hs.z;
-  double ib = fm::rcp(beta1);
-  double xkb = omega * ib;
-  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-  double e1 = (double)hs.w * rb;
-  double e2 = ib * ib;
-  for (int l = L - 2; l >= 0; --l) {
-    LayerRow r = rows[l * stride];
-    double d = (double)r.x;
-    beta1 = (double)r.z;
-    double xmu = (double)r.w * beta1 * beta1;
-    double em;
-    HalfTerms q = half_terms(wvno, omega * fm::rcp(beta1), d, &em);
-    double e10 = e1 * q.cs + e2 * xmu * q.r_sn;
-    double e20 = e1 * q.sn_over_r * fm::rcp(xmu) + e2 * q.cs;
-    double xnor = fm::absmax(e10, e20);
-    if (xnor < 1.0e-40) xnor = 1.0;
-    if (l == 0) return e10 / xnor;          // IEEE division: exact +-1.0 when saturated
-    double inv = fm::rcp(xnor);
-    e1 = e10 * inv;
-    e2 = e20 * inv;
-  }
-  return e1;
+// Love: per-layer terms that do not depend on the propagated vector
+struct LoveLayer { double cs, y_over_mu, mu_z; };
+
+BH_HD LoveLayer love_layer(const double* rec, int fs, double wvno, double omega) {
+  HalfTerms q = half_terms(wvno, omega * rec[LR_IB * fs], rec[LR_D * fs]);
+  LoveLayer m;
+  m.cs = q.cs;
+  m.y_over_mu = q.sn_over_r * rec[LR_IMU * fs];
+  m.mu_z = rec[LR_MU * fs] * q.r_sn;
+  return m;
 }
 
-BH_HD double secular_rayleigh_fast(const LayerRow* rows, int stride, int L, double wvno, double omga) {
+// rec: field f of layer l at rec[f * fs + l * ls]; l = L-1 is the half-space.
+// The layer terms of layer l-1 are computed in the same loop body that applies
+// layer l to the vector: the two are independent, which lets the scheduler hide
+// the serial dot-product / normalisation chain behind the next layer's math.
+BH_HD double secular_love_rec(const double* rec, int fs, int ls, int L, double wvno, double omega) {
+  const double* hs = rec + (L - 1) * ls;
+  double ib = hs[LR_IB * fs];
+  double xkb = omega * ib;
+  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double e1 = hs[LR_D * fs] * rb;     // rho * rb
+  double e2 = ib * ib;
+  if (L < 2) return e1;
+  LoveLayer m = love_layer(rec + (L - 2) * ls, fs, wvno, omega);
+  for (int l = L - 2; l >= 1; --l) {
+    LoveLayer mn = love_layer(rec + (l - 1) * ls, fs, wvno, omega);
+    double e10 = e1 * m.cs + e2 * m.mu_z;
+    double e20 = e1 * m.y_over_mu + e2 * m.cs;
+    double sc = fm::pow2_rescale2(e10, e20);
+    e1 = e10 * sc;
+    e2 = e20 * sc;
+    m = mn;
+  }
+  double e10 = e1 * m.cs + e2 * m.mu_z;
+  double e20 = e1 * m.y_over_mu + e2 * m.cs;
+  double xnor = fm::absmax(e10, e20);
+  if (xnor < 1.0e-40) xnor = 1.0;
+  return e10 / xnor;                         // IEEE division: exact +-1.0 when saturated
+}
+
+// Rayleigh: the distinct entries of Dunkin's compound matrix of one layer
+struct DunkinLayer {
+  double c11, c12, c13, c14, c15, c21, c22, c23, c24, c31, c32, c33, c34, c35, c41, c42, c43, c51, c53;
+};
+
+BH_HD DunkinLayer dunkin_layer(const double* rec, int fs, double wvno, double wvno2, double omega,
+                               double iomega2) {
+  double dpth = rec[RR_D * fs], rho = rec[RR_RHO * fs], rinv = rec[RR_IRHO * fs];
+  double gammk = rec[RR_TB2 * fs] * iomega2;          // 2 (b/omega)^2
+  double gam = gammk * wvno2;
+  HalfTerms P = half_terms(wvno, omega * rec[RR_IA * fs], dpth);
+  HalfTerms S = half_terms(wvno, omega * rec[RR_IB * fs], dpth);
+  double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
+  double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
+  double exa = P.ex + S.ex;
+  double a0 = (exa < 60.0) ? P.em * S.em : 0.0;
+  double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
+  double xy = x * y, xz = x * z, wy = w * y, wz = w * z;
+  double gamm1 = gam - 1.0;
+  double twgm1 = gam + gamm1;
+  double gmgmk = gam * gammk;
+  double gmgm1 = gam * gamm1;
+  double gm1sq = gamm1 * gamm1;
+  double rho2 = rho * rho;
+  double a0pq = a0 - cpcq;
+  DunkinLayer m;
+  m.c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
+  m.c12 = (wvno2 * cpy - cqx) * rinv;
+  m.c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * rinv;
+  m.c14 = (cpz - wvno2 * cqw) * rinv;
+  m.c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * (rinv * rinv);
+  m.c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
+  m.c22 = cpcq;
+  m.c23 = gammk * cpz - gamm1 * cqw;
+  m.c24 = -wz;
+  m.c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
+  m.c42 = -xy;
+  m.c43 = gamm1 * cpy - gammk * cqx;
+  m.c51 = -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
+  m.c53 = -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
+  double tt = -2.0 * wvno2;
+  m.c31 = tt * m.c53; m.c32 = tt * m.c43; m.c33 = a0 + 2.0 * (cpcq - m.c11);
+  m.c34 = tt * m.c23; m.c35 = tt * m.c13;
+  return m;
+}
+
+#define BH_DUNKIN_APPLY(m)                                                          \
+  double n0 = e0 * m.c11 + e1 * m.c21 + e2 * m.c31 + e3 * m.c41 + e4 * m.c51;      \
+  double n1 = e0 * m.c12 + e1 * m.c22 + e2 * m.c32 + e3 * m.c42 + e4 * m.c41;      \
+  double n2 = e0 * m.c13 + e1 * m.c23 + e2 * m.c33 + e3 * m.c43 + e4 * m.c53;      \
+  double n3 = e0 * m.c14 + e1 * m.c24 + e2 * m.c34 + e3 * m.c22 + e4 * m.c21;      \
+  double n4 = e0 * m.c15 + e1 * m.c14 + e2 * m.c35 + e3 * m.c12 + e4 * m.c11;
+
+BH_HD double secular_rayleigh_rec(const double* rec, int fs, int ls, int L, double wvno, double omga) {
   double omega = (omga < 1.0e-4) ? 1.0e-4 : omga;
   double iomega = fm::rcp(omega);
+  double iomega2 = iomega * iomega;
   double wvno2 = wvno * wvno;
   double e0, e1, e2, e3, e4;
   {
-    LayerRow hs = rows[(L - 1) * stride];
-    double a = (double)hs.y, b = (double)hs.z, rho1 = (double)hs.w;
-    double xka = omega * fm::rcp(a), xkb = omega * fm::rcp(b);
+    const double* hs = rec + (L - 1) * ls;
+    double rho1 = hs[RR_RHO * fs];
+    double xka = omega * hs[RR_IA * fs], xkb = omega * hs[RR_IB * fs];
     double ra = sqrt((wvno + xka) * fabs(wvno - xka));
     double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    double t = b * iomega;
-    double gammk = 2.0 * t * t;
+    double gammk = hs[RR_TB2 * fs] * iomega2;
     double gam = gammk * wvno2;
     double gamm1 = gam - 1.0;
     e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
@@ -286,69 +398,64 @@ BH_HD double secular_rayleigh_fast(const LayerRow* rows, int stride, int L, doub
     e3 = rho1 * rb;
     e4 = wvno2 - ra * rb;
   }
-  for (int l = L - 2; l >= 0; --l) {
-    LayerRow r = rows[l * stride];
-    double dpth = (double)r.x, a = (double)r.y, b = (double)r.z, rho = (double)r.w;
-    double t = b * iomega;
-    double gammk = 2.0 * t * t;
-    double gam = gammk * wvno2;
-    double ep, eq;
-    HalfTerms P = half_terms(wvno, omega * fm::rcp(a), dpth, &ep);
-    HalfTerms S = half_terms(wvno, omega * fm::rcp(b), dpth, &eq);
-    double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
-    double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
-    double exa = P.ex + S.ex;
-    double a0 = (exa < 60.0) ? ep * eq : 0.0;
-    double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
-    double xy = x * y, xz = x * z, wy = w * y, wz = w * z;
-    double gamm1 = gam - 1.0;
-    double twgm1 = gam + gamm1;
-    double gmgmk = gam * gammk;
-    double gmgm1 = gam * gamm1;
-    double gm1sq = gamm1 * gamm1;
-    double rho2 = rho * rho;
-    double rinv = fm::rcp(rho);
-    double a0pq = a0 - cpcq;
-    double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
-    double c12 = (wvno2 * cpy - cqx) * rinv;
-    double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * rinv;
-    double c14 = (cpz - wvno2 * cqw) * rinv;
-    double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * (rinv * rinv);
-    double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
-    double c22 = cpcq;
-    double c23 = gammk * cpz - gamm1 * cqw;
-    double c24 = -wz;
-    double c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
-    double c42 = -xy;
-    double c43 = gamm1 * cpy - gammk * cqx;
-    double c51 = -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
-    double c53 = -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
-    double tt = -2.0 * wvno2;
-    double c31 = tt * c53, c32 = tt * c43, c33 = a0 + 2.0 * (cpcq - c11), c34 = tt * c23, c35 = tt * c13;
-    double n0 = e0 * c11 + e1 * c21 + e2 * c31 + e3 * c41 + e4 * c51;
-    double n1 = e0 * c12 + e1 * c22 + e2 * c32 + e3 * c42 + e4 * c41;
-    double n2 = e0 * c13 + e1 * c23 + e2 * c33 + e3 * c43 + e4 * c53;
-    double n3 = e0 * c14 + e1 * c24 + e2 * c34 + e3 * c22 + e4 * c21;
-    double n4 = e0 * c15 + e1 * c14 + e2 * c35 + e3 * c12 + e4 * c11;
-    double t1 = fm::absmax(fm::absmax(fm::absmax(n0, n1), fm::absmax(n2, n3)), n4);
-    if (t1 < 1.0e-40) t1 = 1.0;
-    if (l == 0) return n0 / t1;             // IEEE division: exact +-1.0 when saturated
-    double inv = fm::rcp(t1);
-    e0 = n0 * inv; e1 = n1 * inv; e2 = n2 * inv; e3 = n3 * inv; e4 = n4 * inv;
+  if (L < 2) return e0;
+#if BH_SWD_PAIR
+  // Two layers per iteration: their matrices are independent of each other and
+  // of the propagated vector, so both are formed in one basic block (four
+  // interleaved sqrt/exp/sincos chains for the fp64 pipe), then applied in turn.
+  int l = L - 2;
+  for (; l >= 1; l -= 2) {
+    DunkinLayer ma = dunkin_layer(rec + l * ls, fs, wvno, wvno2, omega, iomega2);
+    DunkinLayer mb = dunkin_layer(rec + (l - 1) * ls, fs, wvno, wvno2, omega, iomega2);
+    {
+      BH_DUNKIN_APPLY(ma)
+      double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
+      e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
+    }
+    BH_DUNKIN_APPLY(mb)
+    if (l == 1) {
+      double t1 = fm::absmax(fm::absmax(fm::absmax(n0, n1), fm::absmax(n2, n3)), n4);
+      if (t1 < 1.0e-40) t1 = 1.0;
+      return n0 / t1;                        // IEEE division: exact +-1.0 when saturated
+    }
+    double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
+    e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
   }
-  return e0;
+  DunkinLayer m = dunkin_layer(rec, fs, wvno, wvno2, omega, iomega2);   // l == 0
+#else
+  DunkinLayer m = dunkin_layer(rec + (L - 2) * ls, fs, wvno, wvno2, omega, iomega2);
+  for (int l = L - 2; l >= 1; --l) {
+    DunkinLayer mn = dunkin_layer(rec + (l - 1) * ls, fs, wvno, wvno2, omega, iomega2);
+    BH_DUNKIN_APPLY(m)
+    double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
+    e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
+    m = mn;
+  }
+#endif
+  BH_DUNKIN_APPLY(m)
+  double t1 = fm::absmax(fm::absmax(fm::absmax(n0, n1), fm::absmax(n2, n3)), n4);
+  if (t1 < 1.0e-40) t1 = 1.0;
+  return n0 / t1;                            // IEEE division: exact +-1.0 when saturated
 }
 
-// BH_SECULAR_REFERENCE_ORDER (tests/host_sim only) selects the formulation that
-// follows the Fortran operation by operation, for bit-equality with the oracle.
+BH_HD double secular_rec(int wave, const double* rec, int fs, int ls, int L, double wvno, double omega) {
+  return wave == 1 ? secular_love_rec(rec, fs, ls, L, wvno, omega)
+                   : secular_rayleigh_rec(rec, fs, ls, L, wvno, omega);
+}
+
+// Row-based entry (host simulation and tests): BH_SECULAR_REFERENCE_ORDER selects
+// the formulation that follows the Fortran operation by operation, for
+// bit-equality with the oracle; otherwise records are derived on the fly and the
+// device formulation above is evaluated.
 BH_HD double secular(int wave /*1 Love, 2 Rayleigh*/, const LayerRow* rows, int stride, int L,
                      double wvno, double omega) {
 #if defined(BH_SECULAR_REFERENCE_ORDER)
   return wave == 1 ? secular_love_reforder(rows, stride, L, wvno, omega)
                    : secular_rayleigh_reforder(rows, stride, L, wvno, omega);
 #else
-  return wave == 1 ? secular_love_fast(rows, stride, L, wvno, omega)
-                   : secular_rayleigh_fast(rows, stride, L, wvno, omega);
+  double rec[SWD_REC_FIELDS * SWD_MAX_LAYERS];
+  for (int l = 0; l < L; ++l) swd_make_rec(wave, rows[l * stride], l == L - 1, rec + l, SWD_MAX_LAYERS);
+  return secular_rec(wave, rec, SWD_MAX_LAYERS, 1, L, wvno, omega);
 #endif
 }
 
@@ -380,42 +487,105 @@ BH_HD float halfspace_start(float a, float b) {
 
 // ---------------------------------------------------------------------------
 // Search state machine
+//
+// A phase-velocity curve is ONE serial chain of root searches: period k starts
+// from c(k-1) - 1.5 dc (surfdisp96.f:268-271).  A group-velocity curve needs two
+// roots per period, at t1a = T/(1+h) and t1b = T/(1-h) (:231-239, :282-294); the
+// reference finds them one after the other, but the data flow is
+//     first root c(k)   <- c(k-1)               (same chain as a phase curve at t1a)
+//     second root cb(k) <- c(k) only            (start c(k) - 1.5 dc, clow = 0.01 dc)
+// so the second roots hang off the first-root chain and never feed back into it
+// (cb(k) is read only for higher modes).  The engine therefore runs a group
+// curve as TWO chains on two lanes: role A searches the first roots and
+// publishes c(k); role B searches the second roots as they become available.
+// Each chain consumes exactly the reference's candidate sequence.
 // ---------------------------------------------------------------------------
 enum SearchStage : int {
   ST_BR_FIRST = 0,   // waiting for del1 = secular(c1)             (getsol :429)
   ST_BR_STEP = 1,    // waiting for del2 at c2 = c1 +- dc           (getsol :448-470)
   ST_RF_TOP = 2,     // waiting for del3; resume at nevill label 100 (:587)
   ST_RF_POST = 3,    // waiting for del3 of the range-fix half (:596); resume at :599
-  ST_DONE = 4,       // all periods found
-  ST_FAILED = 5      // err = 1 (no root for a period of the fundamental mode)
+  ST_WAIT = 4,       // role B: first root of period k not published yet
+  ST_DONE = 5,       // all periods found
+  ST_FAILED = 6      // err = 1 (no root for a period of the fundamental mode)
 };
 
 struct Search {
   // per-search constants
   double cc, dc, betmx;      // start value, dble(0.005f), dble(REAL*4 max vs)
-  int wave, igr, kmax;
+  int kmax, role;            // role 0: first roots (A), 1: second roots of a group curve (B)
   // period bookkeeping
   int k;                     // 0-based period index
-  int second;                // 0: root at t1 (t1a for group), 1: root at t1b
   int stage;
   int ifirst, idir;
-  float t1a, t1b;
   double omega;              // twopi / t1 of the root being searched
   double c1, c2, del1, del2, clow, del1st;
-  double cprev;              // c(k-1)
-  double ck;                 // c(k), first root of the current period
+  double cprev;              // A: c(k-1);  B: c(k) of the period being searched
   // nevill
   double c3, del3;
   int nev, nctrl, m;
   double x[11], y[11];
 };
 
+// What role A publishes for role B (one per group search; shared memory on the device)
+struct SearchLink {
+  int na;          // first roots found so far: B may search periods k < na
+  int a_failed;    // A ended in ST_FAILED
+  double del1st;   // getsol's SAVEd del1st (:415,430), set at the first period
+};
+
+// Per-curve context of one search: period tables and root storage
+struct SearchCtx {
+  const double* omA;   // [kmax] twopi / t1       (phase: t1 = T;  group: t1 = dble(t1a))
+  const double* omB;   // [kmax] twopi / dble(t1b) (group only)
+  double* ra;          // [kmax] first roots c(k)
+  double* rb;          // [kmax] second roots cb(k) (group only)
+  SearchLink* link;    // group only
+};
+
 constexpr double SWD_TWOPI = 2.0 * 3.141592653589793;
+
+// t1a = t1/(1.+h), t1b = t1/(1.-h): REAL*4 sums, REAL*8 quotient, REAL*4 store (:233-235)
+BH_HD void swd_group_periods(double period, float* t1a, float* t1b) {
+  *t1a = (float)(period / (double)fadd(1.0f, 0.005f));
+  *t1b = (float)(period / (double)fsub(1.0f, 0.005f));
+}
+// angular frequencies of the searches of one period (getsol :426: omega = twopi/t1)
+BH_HD void swd_period_omegas(int igr, double period, double* omA, double* omB) {
+  if (igr > 0) {
+    float t1a, t1b;
+    swd_group_periods(period, &t1a, &t1b);
+    *omA = SWD_TWOPI / (double)t1a;
+    *omB = SWD_TWOPI / (double)t1b;
+  } else {
+    *omA = SWD_TWOPI / period;
+    *omB = 0.0;
+  }
+}
+// cg(k) from the stored roots (:298-310): phase = sngl(c(k)); group velocity formula
+// evaluated entirely in REAL*4, each operation rounded
+BH_HD double swd_curve_value(int igr, double period, double ra, double rb) {
+  if (igr <= 0) return (double)(float)ra;
+  float t1a, t1b;
+  swd_group_periods(period, &t1a, &t1b);
+  float cc0 = (float)ra, cc1 = (float)rb;
+  float num = fsub(fdiv(1.0f, t1a), fdiv(1.0f, t1b));
+  float den = fsub(fdiv(1.0f, fmul(t1a, cc0)), fdiv(1.0f, fmul(t1b, cc1)));
+  return (double)fdiv(num, den);
+}
+
+BH_HD bool sign_differs(double a, double b) {   // dsign(1,a) != dsign(1,b), +-0 aware
+#if defined(__CUDA_ARCH__)
+  return (__double2hiint(a) ^ __double2hiint(b)) < 0;
+#else
+  return (signbit(a) != 0) != (signbit(b) != 0);
+#endif
+}
 
 // Extremal velocities + start value (surfdisp96.f:139-156, 197-217).  Water
 // layers (vs <= 0.01) are outside this engine's scope: vs > 0 is enforced by
 // BayHunter's priors (SingleChain.py:358-363); such a model is reported failed.
-BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int wave, int igr, int kmax) {
+BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int kmax, int role) {
   float betmx = -1.e20f, betmn = 1.e20f;
   int jmn = 0;
   bool solid = true;
@@ -425,12 +595,11 @@ BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int 
     else if (r.z <= 0.01f) solid = false;
     if (r.z > betmx) betmx = r.z;
   }
-  s.wave = wave; s.igr = igr; s.kmax = kmax;
+  s.kmax = kmax; s.role = role;
   s.dc = fabs((double)0.005f);
   s.betmx = (double)betmx;
-  s.k = 0; s.second = 0;
-  s.cprev = 0.0; s.ck = 0.0; s.del1st = 0.0;
-  s.t1a = 0.f; s.t1b = 0.f; s.omega = 0.0;
+  s.k = 0;
+  s.cprev = 0.0; s.del1st = 0.0; s.omega = 0.0;
   s.c1 = s.c2 = s.del1 = s.del2 = s.clow = 0.0;
   s.c3 = s.del3 = 0.0; s.nev = 0; s.nctrl = 0; s.m = 0;
   s.ifirst = 0; s.idir = 1;
@@ -440,23 +609,12 @@ BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int 
   cc1 = fmul(.95f, cc1);
   cc1 = fmul(.90f, cc1);
   s.cc = (double)cc1;
-  s.stage = ST_BR_FIRST;
+  s.stage = role ? ST_WAIT : ST_BR_FIRST;
   return true;
 }
 
-// Start the search for period index s.k (first root).  period = t(k).
-BH_HD void search_begin_period(Search& s, double period) {
-  double t1 = period;
-  if (s.igr > 0) {
-    // t1a = t1/(1.+h), t1b = t1/(1.-h): REAL*4 sums, REAL*8 quotient, REAL*4 store (:233-235)
-    s.t1a = (float)(t1 / (double)fadd(1.0f, 0.005f));
-    s.t1b = (float)(t1 / (double)fsub(1.0f, 0.005f));
-    t1 = (double)s.t1a;
-  } else {
-    s.t1a = (float)t1;
-    s.t1b = 0.0f;
-  }
-  s.second = 0;
+// Role A: start the search of period s.k (first root)
+BH_HD void search_begin_a(Search& s, const SearchCtx& ctx) {
   if (s.k == 0) {            // :253-256
     s.c1 = s.cc; s.clow = s.cc; s.ifirst = 1;
   } else {                   // :268-271
@@ -464,8 +622,24 @@ BH_HD void search_begin_period(Search& s, double period) {
     s.c1 = dadd(s.cprev, -dmul(1.5, s.dc));
     s.clow = s.cc;           // clow = cm = cc
   }
-  s.omega = SWD_TWOPI / t1;
+  s.omega = ctx.omA[s.k];
   s.stage = ST_BR_FIRST;
+}
+
+// Role B: start the second root of period s.k if role A has published c(k) (:282-287)
+BH_HD void search_poll_b(Search& s, const SearchCtx& ctx) {
+  if (s.stage != ST_WAIT) return;
+  if (s.k < ctx.link->na) {
+    s.cprev = ctx.ra[s.k];
+    s.del1st = ctx.link->del1st;
+    s.ifirst = 0;
+    s.clow = dmul(1.0e-2, s.dc);                  // cb(k) + one*dc, cb(k) = 0 in the fundamental mode
+    s.c1 = dadd(s.cprev, -dmul(1.5, s.dc));
+    s.omega = ctx.omB[s.k];
+    s.stage = ST_BR_FIRST;
+  } else if (ctx.link->a_failed) {
+    s.stage = ST_FAILED;
+  }
 }
 
 // Next bracket candidate of getsol's loop (:448-458), advancing (c1, idir).
@@ -481,7 +655,7 @@ BH_HD double bracket_next(double& c1, int& idir, double clow, double dc) {
 
 // How many candidates the search can use this round (>= 1 while running).
 BH_HD int search_nwant(const Search& s, int nmax) {
-  if (s.stage >= ST_DONE) return 0;
+  if (s.stage >= ST_WAIT) return 0;
   return s.stage == ST_BR_STEP ? nmax : 1;
 }
 
@@ -506,64 +680,32 @@ BH_HD void nevill_request_half(Search& s, int next_stage) {
   s.stage = next_stage;
 }
 
-// Called when a root c3 has been accepted by nevill (:671-673) and getsol's
-// post-checks (:475-476) are due.  Returns true when the whole curve is done
-// or failed; `out` receives cg(k) when a period completes (out_valid = true).
-BH_HD void search_root_done(Search& s, const double* periods, double* out, bool* out_valid) {
-  double c1 = s.c3;
-  bool ok = !(c1 > s.betmx);                       // :476
-  *out_valid = false;
-  if (s.second == 0) {
-    if (!ok) { s.stage = ST_FAILED; return; }      // :277 -> 1700, err = 1
-    s.ck = c1;                                     // c(k) = c1
-    if (s.igr > 0) {                               // :282-287 second root at t1b
-      s.second = 1;
-      s.ifirst = 0;
-      s.clow = dmul(1.0e-2, s.dc);                // cb(k) + one*dc, cb(k) = 0 in the fundamental mode
-      s.c1 = dadd(c1, -dmul(1.5, s.dc));
-      s.omega = SWD_TWOPI / (double)s.t1b;
-      s.stage = ST_BR_FIRST;
+// The search of the current root ended with value `root`; found = false when
+// getsol gave up (bracket left the window, or root > betmx :476).
+BH_HD void search_root_end(Search& s, const SearchCtx& ctx, double root, bool found) {
+  if (s.role == 0) {
+    if (!found) {                                  // :277 -> 1700, err = 1
+      s.stage = ST_FAILED;
+      if (ctx.link) ctx.link->a_failed = 1;
       return;
     }
-    *out = (double)(float)s.ck;                    // cg(k) = sngl(c(k)) (:298,303)
-    *out_valid = true;
+    ctx.ra[s.k] = root;                            // c(k) = c1
+    s.cprev = root;
+    s.k += 1;
+    if (ctx.link) ctx.link->na = s.k;
+    if (s.k >= s.kmax) { s.stage = ST_DONE; return; }
+    search_begin_a(s, ctx);
   } else {
-    if (!ok) c1 = s.ck;                            // :291-293
-    float cc0 = (float)s.ck, cc1 = (float)c1;
-    // :306 evaluated entirely in REAL*4, each operation rounded
-    float num = fsub(fdiv(1.0f, s.t1a), fdiv(1.0f, s.t1b));
-    float den = fsub(fdiv(1.0f, fmul(s.t1a, cc0)), fdiv(1.0f, fmul(s.t1b, cc1)));
-    *out = (double)fdiv(num, den);
-    *out_valid = true;
+    ctx.rb[s.k] = found ? root : s.cprev;          // :291-293: no second root -> c1 = c(k)
+    s.k += 1;
+    s.stage = (s.k >= s.kmax) ? ST_DONE : ST_WAIT;
+    search_poll_b(s, ctx);
   }
-  // next period
-  s.cprev = s.ck;
-  s.k += 1;
-  if (s.k >= s.kmax) { s.stage = ST_DONE; return; }
-  search_begin_period(s, periods[s.k]);
-}
-
-// Failure inside getsol's bracket loop (:468-469 -> 1700).
-BH_HD void search_bracket_failed(Search& s, const double* periods, double* out, bool* out_valid) {
-  *out_valid = false;
-  if (s.second == 0) { s.stage = ST_FAILED; return; }
-  // second root of a group-velocity period not found: reuse c(k) (:291-293)
-  s.c3 = s.ck;
-  // betmx check was on getsol's own root; here c1 = c(k) unconditionally
-  float cc0 = (float)s.ck, cc1 = (float)s.ck;
-  float num = fsub(fdiv(1.0f, s.t1a), fdiv(1.0f, s.t1b));
-  float den = fsub(fdiv(1.0f, fmul(s.t1a, cc0)), fdiv(1.0f, fmul(s.t1b, cc1)));
-  *out = (double)fdiv(num, den);
-  *out_valid = true;
-  s.cprev = s.ck;
-  s.k += 1;
-  if (s.k >= s.kmax) { s.stage = ST_DONE; return; }
-  search_begin_period(s, periods[s.k]);
 }
 
 // nevill main loop from label 100 (:587) until the next secular evaluation is
-// needed (returns with stage = ST_RF_TOP / ST_RF_POST and c3 set) or the root
-// is accepted (returns true).
+// needed (returns false with stage = ST_RF_TOP / ST_RF_POST and c3 set) or the
+// root is accepted (returns true).
 BH_HD bool nevill_resume(Search& s, bool at_top) {
   for (;;) {
     if (at_top) {
@@ -578,10 +720,10 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
     at_top = true;
     double s13 = s.del1 - s.del3;
     double s32 = s.del3 - s.del2;
-    if (sign1(s.del3) * sign1(s.del1) < 0.0) { s.c2 = s.c3; s.del2 = s.del3; }   // :604-610
+    if (sign_differs(s.del3, s.del1)) { s.c2 = s.c3; s.del2 = s.del3; }  // :604-610
     else { s.c1 = s.c3; s.del1 = s.del3; }
     if (fabs(s.c1 - s.c2) <= 1.0e-6 * s.c1) return true;                 // :614
-    if (sign1(s13) != sign1(s32)) s.nev = 0;                             // :619
+    if (sign_differs(s13, s32)) s.nev = 0;                               // :619
     double ss1 = fabs(s.del1);
     double s1 = (double)0.01f * ss1;                                     // REAL*4 literal (:625)
     double ss2 = fabs(s.del2);
@@ -605,7 +747,7 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
       int j = s.m - kk;
       double denom = s.y[s.m] - s.y[j];
       if (fabs(denom) < 1.0e-10 * fabs(s.y[s.m])) { bad = true; break; }
-      s.x[j] = (-s.y[j] * s.x[j + 1] + s.y[s.m] * s.x[j]) / denom;
+      s.x[j] = fm::div(-s.y[j] * s.x[j + 1] + s.y[s.m] * s.x[j], denom);
     }
     if (bad) {                                                           // :663-667
       nevill_request_half(s, ST_RF_TOP);
@@ -623,21 +765,18 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
 }
 
 // Consume n secular values del[0..n) for the candidates this search published
-// this round (n = 1 unless stage == ST_BR_STEP).  `periods` is the period
-// vector of the curve; finished velocities are stored through `emit(k, value)`.
-// Returns how many of the n values were consumed (the rest was speculation
-// past a sign change or past the search window).
-template <class Emit>
-BH_HD int search_consume(Search& s, const double* del, int n, const double* periods, Emit emit) {
-  double out = 0.0;
-  bool out_valid = false;
-  int kdone = s.k;
+// this round (n = 1 unless stage == ST_BR_STEP).  Returns how many of the n
+// values were consumed (the rest was speculation past a sign change or past
+// the search window).
+BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& ctx) {
   switch (s.stage) {
     case ST_BR_FIRST: {
       s.del1 = del[0];
-      if (s.ifirst == 1) s.del1st = s.del1;                              // :430
-      double plmn = sign1(s.del1st) * sign1(s.del1);
-      s.idir = (s.ifirst == 1 || plmn >= 0.0) ? +1 : -1;                 // :432-438
+      if (s.ifirst == 1) {                                               // :430
+        s.del1st = s.del1;
+        if (ctx.link) ctx.link->del1st = s.del1;
+      }
+      s.idir = (s.ifirst == 1 || !sign_differs(s.del1st, s.del1)) ? +1 : -1;   // :432-438
       s.stage = ST_BR_STEP;
       return 1;
     }
@@ -645,7 +784,7 @@ BH_HD int search_consume(Search& s, const double* del, int n, const double* peri
       for (int i = 0; i < n; ++i) {
         s.c2 = bracket_next(s.c1, s.idir, s.clow, s.dc);
         s.del2 = del[i];
-        if (sign1(s.del1) != sign1(s.del2)) {                            // :462 -> nevill
+        if (sign_differs(s.del1, s.del2)) {                              // :462 -> nevill
           nevill_request_half(s, ST_RF_TOP);                             // :583
           s.nev = 1;
           s.nctrl = 1;
@@ -654,8 +793,7 @@ BH_HD int search_consume(Search& s, const double* del, int n, const double* peri
         s.c1 = s.c2;
         s.del1 = s.del2;
         if (s.c1 < s.cc || s.c1 >= (s.betmx + s.dc)) {                   // :468-469 (cm = cc)
-          search_bracket_failed(s, periods, &out, &out_valid);
-          if (out_valid) emit(kdone, out);
+          search_root_end(s, ctx, 0.0, false);
           return i + 1;
         }
       }
@@ -664,10 +802,8 @@ BH_HD int search_consume(Search& s, const double* del, int n, const double* peri
     case ST_RF_TOP:
     case ST_RF_POST: {
       s.del3 = del[0];
-      if (nevill_resume(s, s.stage == ST_RF_TOP)) {
-        search_root_done(s, periods, &out, &out_valid);
-        if (out_valid) emit(kdone, out);
-      }
+      if (nevill_resume(s, s.stage == ST_RF_TOP))
+        search_root_end(s, ctx, s.c3, !(s.c3 > s.betmx));                // :475-476
       return 1;
     }
     default:

@@ -1,40 +1,40 @@
 // swd_kernel.cu -- batched SURF96-equivalent dispersion search on sm_100a.
 //
-// Mapping: a warp owns up to S searches (one search = one dispersion curve of
-// one model; S = searches_per_warp).  Lane s < S keeps search s's state machine
-// in registers.  Every round the 32 lanes of the warp are dealt out to the
-// pending secular-function candidates of those searches: one lane for a search
-// that is refining a root (the reference's Neville/bisection sequence is
-// strictly serial), and the spare lanes to the searches that are still walking
-// their bracket (candidates c1+dc, c1+2dc, ... are independent of earlier
-// secular values, so evaluating them ahead is pure speculation that cannot
-// change the result).  All lanes then run the secular function together -- the
-// only expensive, and fully convergent, part of the kernel.
+// Mapping: one warp per CTA; a warp owns up to S models of ONE curve.  A phase
+// curve is one serial chain of root searches per model (lane m < S keeps its
+// state machine in registers); a group curve is two chains per model -- first
+// roots on lane m, second roots on lane S + m, see swd_core.cuh -- so S <= 16
+// there.  Every round the 32 lanes of the warp are dealt out to the pending
+// secular-function candidates of those chains: one lane for a chain that is
+// refining a root (the reference's Neville/bisection sequence is strictly
+// serial), and the spare lanes to the chains that are still walking their
+// bracket (candidates c1+dc, c1+2dc, ... are independent of earlier secular
+// values, so evaluating them ahead is pure speculation that cannot change the
+// result).  All lanes then run the secular function together -- the only
+// expensive, and fully convergent, part of the kernel.
 //
-// Model rows are staged once per warp into shared memory as REAL*4 float4 rows
-// (exactly the precision SURF96 sees); the row stride is odd so that the
-// float4 reads of 8 consecutive lanes hit 8 distinct 16-byte bank groups.
+// Shared memory per warp: the fp64 layer records of its S models
+// (swd_core.cuh: swd_make_rec), field-major [field][layer][search] so that the
+// 32 lanes of a round read 32 distinct banks (or broadcast when several lanes
+// speculate for the same search), plus one small mailbox (WarpShared).
 #include "kernels.h"
 
 namespace bh {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
-
 struct WarpShared {
   double c[32];       // pending candidate base (c1 or c3) per owner
   double clow[32];
   double omega[32];
   double del[32];     // secular values per lane
+  double omA[SWD_MAX_PERIODS], omB[SWD_MAX_PERIODS];   // per-period angular frequencies of this curve
+  SearchLink link[16];                                 // role A -> role B mailboxes (group curves)
   int stage[32];
   int idir[32];
   int nlay[32];       // rows of the owner's model (constant per warp)
-};
-
-struct CurveEmit {
-  double* dst;
-  __device__ __forceinline__ void operator()(int k, double v) const { dst[k] = v; }
+  int col[32];        // record column (model slot) of the owner
+  int owner_at[32];   // owner lane of the candidate run that starts at this lane
 };
 
 __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
@@ -46,64 +46,90 @@ __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(32)
 swd_kernel(SwdLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int S = p.searches_per_warp;
-  const int warps_per_curve = (p.B + S - 1) / S;
-  const int gw = blockIdx.x * kWarpsPerBlock + wib;   // global warp id
-  const int curve = gw / warps_per_curve;
-  if (curve >= p.ncurves) return;                     // whole warp exits together
-  const int b0 = (gw - curve * warps_per_curve) * S;  // first model of this warp
+  const int lane = threadIdx.x;
+  const int gw = blockIdx.x;                          // global warp id
+  int curve = 0;
+  while (curve + 1 < p.ncurves && gw >= p.warp_begin[curve + 1]) ++curve;
+  const int S = p.spw[curve];                         // models per warp (<= 16 for group curves)
+  const int b0 = (gw - p.warp_begin[curve]) * S;      // first model of this warp
   const int nsearch = min(S, p.B - b0);
-
-  // ---- shared-memory carve-up: per warp [rows S*stride][WarpShared] ----
-  const int stride = p.row_stride;
-  const size_t rows_bytes = ((size_t)S * stride * sizeof(LayerRow) + 15) & ~size_t(15);
-  const size_t per_warp = rows_bytes + sizeof(WarpShared);
-  unsigned char* base = smem_raw + per_warp * wib;
-  LayerRow* rows = reinterpret_cast<LayerRow*>(base);
-  WarpShared* ws = reinterpret_cast<WarpShared*>(base + rows_bytes);
-
-  // ---- stage the model rows of this warp's models (coalesced 16 B loads) ----
-  {
-    const LayerRow* src = p.rows + (size_t)b0 * stride;
-    const int total = nsearch * stride;
-    for (int i = lane; i < total; i += 32) rows[i] = src[i];
-  }
-  __syncwarp();
-
   const int wave = p.wave[curve], igr = p.igr[curve], kmax = p.kmax[curve];
   const double* __restrict__ periods = p.periods[curve];
   const int tid = p.target_id[curve];
+  const int stride = p.row_stride;                    // rows per model in p.rows
+  const int lcap = p.lcap;                            // layer capacity of the records
 
-  // ---- owner state ----
+  // ---- shared-memory carve-up: [records 6*lcap*S doubles][WarpShared] ----
+  double* rec = reinterpret_cast<double*>(smem_raw);
+  const int fs = lcap * S;                            // field stride; layer stride = S
+  WarpShared* ws = reinterpret_cast<WarpShared*>(rec + (size_t)SWD_REC_FIELDS * fs);
+
+  // ---- per-period tables of this curve ----
+  for (int k = lane; k < kmax; k += 32) swd_period_omegas(igr, periods[k], &ws->omA[k], &ws->omB[k]);
+  if (lane < 16) { ws->link[lane].na = 0; ws->link[lane].a_failed = 0; ws->link[lane].del1st = 0.0; }
+
+  // ---- owner state: lanes [0, nsearch) run the first-root chains (role A), lanes
+  //      [S, S + nsearch) the second-root chains of group curves (role B) ----
+  const int role = (igr > 0 && lane >= S) ? 1 : 0;
+  const int sidx = role ? lane - S : lane;            // model slot within the warp
+  const bool owner = sidx < nsearch && (role == 0 || igr > 0) && lane < (igr > 0 ? 2 * S : S);
   Search s;
+  SearchCtx ctx;
+  ctx.omA = ws->omA; ctx.omB = ws->omB;
+  ctx.link = (igr > 0 && owner) ? &ws->link[sidx] : nullptr;
+  {
+    double* r = p.roots + ((size_t)(b0 + (owner ? sidx : 0)) * p.curve_stride + p.curve_off[curve]) * 2;
+    ctx.ra = r; ctx.rb = r + kmax;
+  }
   int myL = 0;
-  bool owner = lane < nsearch;
+  __syncwarp();
   if (owner) {
-    myL = p.nlay[b0 + lane];
-    if (myL > stride) myL = stride;
-    if (search_setup(s, rows + lane * stride, 1, myL, wave, igr, kmax))
-      search_begin_period(s, periods[0]);
+    myL = p.nlay[b0 + sidx];
+    if (myL > lcap) myL = lcap;
+    if (search_setup(s, p.rows + (size_t)(b0 + sidx) * stride, 1, myL, kmax, role)) {
+      if (role == 0) search_begin_a(s, ctx);
+    } else if (role == 0 && ctx.link) {
+      ctx.link->a_failed = 1;
+    }
   } else {
     s.stage = ST_DONE;
   }
   ws->nlay[lane] = myL;
+  ws->col[lane] = sidx;
   __syncwarp();
-  double* __restrict__ my_curve =
-      p.curves + (size_t)(b0 + (owner ? lane : 0)) * p.curve_stride + p.curve_off[curve];
+
+  // ---- derive the fp64 layer records of this warp's models ----
+  for (int t = lane; t < lcap * S; t += 32) {
+    const int m = t % S, l = t / S;
+    if (m < nsearch) {
+      const int L = ws->nlay[m];
+      if (l < L) {
+        const LayerRow r = p.rows[(size_t)(b0 + m) * stride + l];
+        swd_make_rec(wave, r, l == L - 1, rec + (size_t)l * S + m, fs);
+      }
+    }
+  }
+  __syncwarp();
 
   unsigned long long consumed = 0, evaluated = 0;
   const int max_spec = p.max_spec;
+  const double dc = fabs((double)0.005f);
 
   for (;;) {
     // ---- phase A: owners publish, warp deals lanes ----
-    int want = owner ? search_nwant(s, 32) : 0;
+    if (role) search_poll_b(s, ctx);
+    int want = search_nwant(s, 32);
     unsigned active = __ballot_sync(0xffffffffu, want > 0);
-    if (active == 0) break;
+    if (active == 0) {
+      // nothing to evaluate: finished, unless a role-B chain is still waiting for a
+      // root that role A published in this very round
+      if (__ballot_sync(0xffffffffu, s.stage == ST_WAIT) == 0) break;
+      __syncwarp();
+      continue;
+    }
     unsigned bracket = __ballot_sync(0xffffffffu, want > 1);
     int nact = __popc(active), nbr = __popc(bracket);
     int extra = 32 - nact;
@@ -126,6 +152,7 @@ swd_kernel(SwdLaunch p) {
     unsigned excl = incl - cnt;
     unsigned total = __shfl_sync(0xffffffffu, incl, 31);
     unsigned startmask = __reduce_or_sync(0xffffffffu, cnt > 0 ? (1u << excl) : 0u);
+    if (cnt > 0) ws->owner_at[excl] = lane;
     __syncwarp();
 
     // ---- phase B: every dealt lane evaluates one candidate ----
@@ -133,27 +160,37 @@ swd_kernel(SwdLaunch p) {
       unsigned below = startmask & (0xffffffffu >> (31 - lane));
       int start = 31 - __clz(below);
       int i = lane - start;
-      int rank = __popc(below) - 1;
-      int own = __fns(active, 0, rank + 1);
+      int own = ws->owner_at[start];
       double omega = ws->omega[own];
-      double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own],
-                                fabs((double)0.005f), i);
+      double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i);
       int L = ws->nlay[own];
-      double wvno = omega / c;
-      ws->del[lane] = secular(wave, rows + own * stride, 1, L, wvno, omega);
+      double wvno = fm::div(omega, c);
+      ws->del[lane] = secular_rec(wave, rec + ws->col[own], fs, S, L, wvno, omega);
       evaluated += 1;
     }
     __syncwarp();
 
     // ---- phase C: owners consume their values in reference order ----
-    if (cnt > 0) {
-      CurveEmit emit{my_curve};
-      consumed += search_consume(s, &ws->del[excl], cnt, periods, emit);
-    }
+    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx);
     __syncwarp();
   }
 
-  if (owner) p.tstatus[(size_t)(b0 + lane) * kMaxTargets + tid] = (s.stage == ST_DONE) ? 1 : 0;
+  // ---- curve values from the stored roots; validity flag ----
+  // role-A lanes write the curve; the second roots of a group curve were stored by
+  // the role-B lane S places up (same warp: ordered by the __syncwarp above)
+  {
+    const bool done = s.stage == ST_DONE;
+    const unsigned bdone = __ballot_sync(0xffffffffu, done);
+    if (owner && role == 0) {
+      bool ok = done;
+      if (igr > 0) ok = ok && ((bdone >> (lane + S)) & 1u);
+      double* __restrict__ my_curve = p.curves + (size_t)(b0 + sidx) * p.curve_stride + p.curve_off[curve];
+      if (ok)
+        for (int k = 0; k < kmax; ++k)
+          my_curve[k] = swd_curve_value(igr, periods[k], ctx.ra[k], igr > 0 ? ctx.rb[k] : 0.0);
+      p.tstatus[(size_t)(b0 + sidx) * kMaxTargets + tid] = ok ? 1 : 0;
+    }
+  }
 
   // ---- counters (one atomic per warp) ----
   for (int d = 16; d > 0; d >>= 1) {
@@ -168,20 +205,26 @@ swd_kernel(SwdLaunch p) {
 
 }  // namespace
 
-void launch_swd(const SwdLaunch& p, cudaStream_t st) {
+size_t swd_smem_bytes(int lcap, int S) {
+  return (size_t)SWD_REC_FIELDS * lcap * S * sizeof(double) + sizeof(WarpShared);
+}
+
+void launch_swd(SwdLaunch& p, cudaStream_t st) {
   if (p.ncurves <= 0 || p.B <= 0) return;
-  const int S = p.searches_per_warp;
-  const int warps_per_curve = (p.B + S - 1) / S;
-  const int warps = warps_per_curve * p.ncurves;
-  const int blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const size_t rows_bytes = ((size_t)S * p.row_stride * sizeof(LayerRow) + 15) & ~size_t(15);
-  const size_t smem = (rows_bytes + sizeof(WarpShared)) * kWarpsPerBlock;
+  int warps = 0, smax = 1;
+  for (int c = 0; c < p.ncurves; ++c) {
+    p.warp_begin[c] = warps;
+    warps += (p.B + p.spw[c] - 1) / p.spw[c];
+    if (p.spw[c] > smax) smax = p.spw[c];
+  }
+  p.warp_begin[p.ncurves] = warps;
+  const size_t smem = swd_smem_bytes(p.lcap, smax);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(swd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  swd_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(p);
+  swd_kernel<<<warps, 32, smem, st>>>(p);
 }
 
 }  // namespace bh

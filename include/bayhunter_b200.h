@@ -106,7 +106,8 @@ void bh_engine_destroy(bh_engine* e);
 int bh_engine_synth_stride(const bh_engine* e);
 
 /* Tunables (call before eval; all have working defaults).
- *   key "swd_searches_per_warp"  1..32   (default chosen from the batch size)
+ *   key "swd_searches_per_warp"  1..32   phase-velocity curves (default chosen from the batch size)
+ *   key "swd_group_searches_per_warp" 1..32  group-velocity curves (default: half of the above)
  *   key "swd_max_spec"           1..32   speculative bracket candidates per search
  *   key "concurrent"             0/1     run SWD and RF kernels on forked streams
  *   key "profile"                0/1     record per-kernel event timings */

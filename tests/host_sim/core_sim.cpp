@@ -14,10 +14,6 @@
 using namespace bh;
 
 namespace {
-struct Emit {
-  double* dst;
-  void operator()(int k, double v) const { dst[k] = v; }
-};
 uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 }  // namespace
 
@@ -27,6 +23,8 @@ extern "C" {
 // spec_mode: 0 -> one candidate per round (reference order), k > 0 -> fixed k
 // speculative bracket candidates per round, < 0 -> random 1..32 per round.
 // counts[0] consumed, counts[1] evaluated secular values.
+// A group curve runs as two chains (first roots / second roots) in lock step,
+// exactly like two lanes of the kernel's warp.
 int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, const double* periods,
                   int spec_mode, unsigned seed, double* cg, long long* counts) {
   std::vector<LayerRow> rows(nlayer);
@@ -35,24 +33,43 @@ int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, c
     rows[i].z = rows4[4 * i + 2]; rows[i].w = rows4[4 * i + 3];
   }
   for (int k = 0; k < kmax; ++k) cg[k] = 0.0;
-  Search s;
+  double omA[SWD_MAX_PERIODS], omB[SWD_MAX_PERIODS], ra[SWD_MAX_PERIODS], rb[SWD_MAX_PERIODS];
+  for (int k = 0; k < kmax; ++k) { swd_period_omegas(igr, periods[k], &omA[k], &omB[k]); ra[k] = rb[k] = 0.0; }
+  SearchLink link; link.na = 0; link.a_failed = 0; link.del1st = 0.0;
+  SearchCtx ctx; ctx.omA = omA; ctx.omB = omB; ctx.ra = ra; ctx.rb = rb; ctx.link = igr > 0 ? &link : nullptr;
+  Search m[2];
   long long consumed = 0, evaluated = 0;
-  if (search_setup(s, rows.data(), 1, nlayer, wave, igr, kmax)) search_begin_period(s, periods[0]);
+  if (search_setup(m[0], rows.data(), 1, nlayer, kmax, 0)) search_begin_a(m[0], ctx);
+  else link.a_failed = 1;
+  if (igr > 0) search_setup(m[1], rows.data(), 1, nlayer, kmax, 1);
+  else m[1].stage = ST_DONE;
   uint32_t rng = seed;
-  double del[32];
-  while (s.stage < ST_DONE) {
-    int nmax = spec_mode == 0 ? 1 : (spec_mode > 0 ? spec_mode : 1 + (int)(lcg(rng) % 32));
-    int n = search_nwant(s, nmax);
-    double cpub = search_pending_c(s);
-    for (int i = 0; i < n; ++i) {
-      double c = candidate_from(s.stage, cpub, s.idir, s.clow, s.dc, i);
-      del[i] = secular(wave, rows.data(), 1, nlayer, s.omega / c, s.omega);
-      ++evaluated;
+  double del[2][32];
+  int n[2];
+  for (;;) {
+    if (igr > 0) search_poll_b(m[1], ctx);
+    int any = 0;
+    for (int r = 0; r < 2; ++r) {
+      Search& s = m[r];
+      int nmax = spec_mode == 0 ? 1 : (spec_mode > 0 ? spec_mode : 1 + (int)(lcg(rng) % 32));
+      n[r] = search_nwant(s, nmax);
+      any += n[r];
+      double cpub = search_pending_c(s);
+      for (int i = 0; i < n[r]; ++i) {
+        double c = candidate_from(s.stage, cpub, s.idir, s.clow, s.dc, i);
+        del[r][i] = secular(wave, rows.data(), 1, nlayer, s.omega / c, s.omega);
+        ++evaluated;
+      }
     }
-    consumed += search_consume(s, del, n, periods, Emit{cg});
+    if (!any) break;
+    for (int r = 0; r < 2; ++r)
+      if (n[r] > 0) consumed += search_consume(m[r], del[r], n[r], ctx);
   }
   if (counts) { counts[0] = consumed; counts[1] = evaluated; }
-  return s.stage == ST_DONE ? 0 : 1;   // err like surfdisp96
+  const bool ok = m[0].stage == ST_DONE && (igr <= 0 || m[1].stage == ST_DONE);
+  if (ok)
+    for (int k = 0; k < kmax; ++k) cg[k] = swd_curve_value(igr, periods[k], ra[k], rb[k]);
+  return ok ? 0 : 1;   // err like surfdisp96
 }
 
 // Receiver function through rf_core.cuh; same arguments as synrf_cwrap minus fz/fr.

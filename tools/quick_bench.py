@@ -1,5 +1,10 @@
-"""Developer probe: per-kernel timings for a config under several tunables (not the bench contract)."""
-import sys, os, time, json
+"""Developer probe: per-kernel timings for a config under several tunables (not the bench contract).
+
+  python tools/quick_bench.py <cfg> <B> [key=value,key=value ...]...
+
+Each further argument is one setting (comma separated engine tunables); with none, a default sweep
+runs.  BH_B200_LIB selects the library build (see bayhunter_b200/_lib.py)."""
+import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bayhunter_b200 as bh
@@ -26,8 +31,13 @@ def run(cfg, B, settings, reps=3):
     eng, rows, nlay, noise = make_engine(cfg, B)
     dev = torch.device("cuda:0")
     tr, tn, tz = (torch.from_numpy(a).to(dev) for a in (rows, nlay, noise))
+    ref = None
     for st in settings:
-        eng.set(profile=1, **st)
+        try:
+            eng.set(profile=1, **st)
+        except Exception as ex:      # older library builds do not know every tunable
+            print(json.dumps(dict(cfg=cfg, skipped=st, why=str(ex))), flush=True)
+            continue
         best = None
         for r in range(reps):
             torch.cuda.synchronize()
@@ -40,23 +50,31 @@ def run(cfg, B, settings, reps=3):
             if best is None or ms < best[0]:
                 best = (ms, k)
         cons, ev = eng.last_counts()
+        logL = out[0].cpu().numpy()
+        if ref is None:
+            ref = logL
+        same = bool(np.array_equal(ref, logL, equal_nan=True))
         print(json.dumps(dict(cfg=cfg, B=B, **st, total_ms=round(best[0], 3),
                               evals_per_s=round(B / best[0] * 1e3), kernels={a: round(b, 3) for a, b in best[1].items()},
-                              consumed=cons, evaluated=ev, valid=float(out[2].float().mean()))), flush=True)
+                              consumed=cons, evaluated=ev, valid=float(out[2].float().mean()),
+                              logL_sum=float(np.nansum(logL)), same_as_first=same)), flush=True)
+
+
+def parse(arg):
+    d = {}
+    for kv in arg.split(","):
+        k, v = kv.split("=")
+        d[k] = int(v)
+    return d
 
 
 if __name__ == "__main__":
-    which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which == "one":      # one setting, for ncu: tools/quick_bench.py one <cfg> <B> <spw> <spec> <conc>
-        cfg, B, spw, spec, conc = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
-        run(cfg, B, [dict(swd_searches_per_warp=spw, swd_max_spec=spec, concurrent=conc)], reps=2)
-    if which in ("all", "joint5"):
-        run("joint5", 8192, [dict(swd_searches_per_warp=s, swd_max_spec=m, concurrent=c)
-                             for (s, m, c) in ((32, 1, 0), (32, 8, 0), (16, 8, 0), (8, 8, 0), (4, 8, 0),
-                                               (32, 8, 1), (16, 8, 1), (8, 8, 1), (16, 4, 1), (16, 16, 1))])
-    if which in ("all", "swd2"):
-        run("swd2", 4096, [dict(swd_searches_per_warp=s, swd_max_spec=m, concurrent=0)
-                           for (s, m) in ((32, 1), (32, 8), (16, 8), (8, 8), (4, 8), (2, 8), (4, 4), (4, 16), (2, 16), (1, 32))])
-    if which in ("all", "transd3"):
-        run("transd3", 4096, [dict(swd_searches_per_warp=s, swd_max_spec=m, concurrent=c)
-                              for (s, m, c) in ((32, 8, 0), (8, 8, 0), (8, 8, 1), (4, 8, 1))])
+    cfg = sys.argv[1] if len(sys.argv) > 1 else "joint5"
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else synthetic.CONFIGS[cfg]["B"]
+    settings = [parse(a) for a in sys.argv[3:]]
+    if not settings:
+        settings = [dict(swd_searches_per_warp=s, swd_group_searches_per_warp=g, swd_max_spec=m, concurrent=c)
+                    for (s, g, m, c) in ((32, 32, 8, 0), (32, 16, 8, 0), (16, 16, 8, 0), (16, 8, 8, 0), (8, 8, 8, 0),
+                                         (32, 16, 8, 1), (16, 8, 8, 1), (16, 8, 4, 1), (16, 8, 16, 1))]
+    print("# lib:", os.environ.get("BH_B200_LIB", "default"), flush=True)
+    run(cfg, B, settings)
