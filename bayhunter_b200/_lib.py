@@ -19,7 +19,8 @@ BH_ERR_ARG, BH_ERR_CUDA, BH_ERR_UNSUPPORTED, BH_ERR_NO_DEVICE = -1, -2, -3, -4
 REF_CODES = {"rdispph": 0, "rdispgr": 1, "ldispph": 2, "ldispgr": 3, "prf": 4, "srf": 5}
 COV_EXP, COV_WHITE, COV_WHITE_SCALED, COV_GAUSS = 0, 1, 2, 3
 MAX_TARGETS, MAX_PERIODS, MAX_LAYERS = 8, 60, 100
-KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik")
+NUM_COUNTERS = 2 + 2 * MAX_TARGETS
+KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik", "swd_love")
 
 
 class BhTarget(ctypes.Structure):

@@ -72,17 +72,22 @@ struct bh_engine {
   double* rfsynth = nullptr;
   int* tstatus = nullptr;
   unsigned long long* counters = nullptr;
+  int* swd_queue = nullptr;   // work-item counters of the mixed dispersion launch
+  int nsm = 0;
   int max_nfreq = 0;
   // device mirrors for the host-pointer entry point
   double *d_model = nullptr, *d_noise = nullptr, *d_rho = nullptr, *d_logL = nullptr,
          *d_misfits = nullptr, *d_synth = nullptr;
   int *d_nlay = nullptr, *d_status = nullptr;
-  cudaStream_t s_own = nullptr, s_aux = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s_own = nullptr, s_aux = nullptr, s_aux2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_fork2 = nullptr;
   // tunables
   int searches_per_warp = 0;  // phase-velocity curves; 0 = auto
   int group_spw = 0;          // group-velocity curves; 0 = half of the above
   int max_spec = 8;
+  int split_waves = 0;        // 1: Rayleigh and Love curves in separate launches (two streams)
+  int rayleigh_sm_pct = 0;    // mixed launch: share of the SMs dedicated to the Rayleigh items (0 = no partition)
+  int direct = 0;             // 0 never, 1 when warps are full of chains, 2 always
   int concurrent = 1;
   // optional per-kernel timing (bh_engine_set "profile"): event pairs around
   // each launch, recorded on the stream the kernel is launched on
@@ -136,8 +141,11 @@ void bh_engine_destroy(bh_engine* e) {
   for (cudaEvent_t ev : e->pev) if (ev) cudaEventDestroy(ev);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+  if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->s_own) cudaStreamDestroy(e->s_own);
   if (e->s_aux) cudaStreamDestroy(e->s_aux);
+  if (e->s_aux2) cudaStreamDestroy(e->s_aux2);
   delete e;
 }
 
@@ -241,7 +249,13 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
   if (rc == BH_OK) rc = scratch(e, &e->roots, 2 * B * e->curve_stride);
   if (rc == BH_OK) rc = scratch(e, &e->rfsynth, B * (size_t)off);
   if (rc == BH_OK) rc = scratch(e, &e->tstatus, B * kMaxTargets);
-  if (rc == BH_OK) rc = scratch(e, &e->counters, 2);
+  if (rc == BH_OK) rc = scratch(e, &e->counters, BH_NUM_COUNTERS);
+  if (rc == BH_OK) rc = scratch(e, &e->swd_queue, 2 + 1024);
+  if (rc == BH_OK) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&e->nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
   if (rc == BH_OK) rc = scratch(e, &e->d_model, B * L * 4);
   if (rc == BH_OK) rc = scratch(e, &e->d_nlay, B);
   if (rc == BH_OK) rc = scratch(e, &e->d_noise, B * 2 * ntargets);
@@ -254,11 +268,14 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
     cudaError_t ce;
     if ((ce = cudaStreamCreateWithFlags(&e->s_own, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&e->s_aux2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming)) != cudaSuccess ||
         (ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (ce = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming)) != cudaSuccess)
       rc = set_err(BH_ERR_CUDA, "stream/event creation", ce);
   }
-  if (rc == BH_OK && cudaMemset(e->counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
+  if (rc == BH_OK && cudaMemset(e->counters, 0, BH_NUM_COUNTERS * sizeof(unsigned long long)) != cudaSuccess)
     rc = set_err(BH_ERR_CUDA, "cudaMemset(counters)");
   if (rc != BH_OK) { std::string keep = g_err; bh_engine_destroy(e); g_err = keep; return rc; }
   *out = e;
@@ -278,6 +295,14 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "swd_max_spec")) {
     if (value < 1 || value > 32) return set_err(BH_ERR_ARG, "swd_max_spec must be 1..32");
     e->max_spec = value;
+  } else if (!strcmp(key, "swd_rayleigh_sm_pct")) {
+    if (value < 0 || value > 100) return set_err(BH_ERR_ARG, "swd_rayleigh_sm_pct must be 0..100");
+    e->rayleigh_sm_pct = value;
+  } else if (!strcmp(key, "swd_split_waves")) {
+    e->split_waves = value ? 1 : 0;
+  } else if (!strcmp(key, "swd_direct")) {
+    if (value < 0 || value > 2) return set_err(BH_ERR_ARG, "swd_direct must be 0, 1 or 2");
+    e->direct = value;
   } else if (!strcmp(key, "concurrent")) {
     e->concurrent = value ? 1 : 0;
   } else if (!strcmp(key, "profile")) {
@@ -301,12 +326,13 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   cudaStream_t st = (cudaStream_t)stream;
   const TargetSet& ts = e->ts;
 
-  SwdLaunch sw{};
+  // one launch per wave type (Rayleigh, Love); inside a launch the curves with the
+  // longer serial chains come first (group before phase)
+  SwdLaunch swl[2] = {};
   int first_rf = -1;
-  // curves in order of decreasing serial work so that the longest chains start
-  // first: Rayleigh group, Rayleigh phase, Love group, Love phase
   for (int pass = 0; pass < 4; ++pass) {
     const int want_wave = pass < 2 ? 2 : 1, want_igr = (pass & 1) ? 0 : 1;
+    SwdLaunch& sw = swl[pass < 2 ? 0 : 1];
     for (int t = 0; t < ts.ntargets; ++t) {
       const TargetDev& d = ts.t[t];
       if (!is_swd(d.ref) || d.wave != want_wave || d.igr != want_igr) continue;
@@ -315,45 +341,87 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       sw.periods[c] = d.periods; sw.curve_off[c] = e->curve_off[t]; sw.synth_off[c] = d.synth_off;
     }
   }
+  const int nswd = swl[0].ncurves + swl[1].ncurves;
+  if (!e->split_waves && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
+    // one mixed launch: append the Love curves to the Rayleigh launch
+    SwdLaunch& a = swl[0];
+    const SwdLaunch& b = swl[1];
+    for (int c = 0; c < b.ncurves; ++c) {
+      int k = a.ncurves++;
+      a.target_id[k] = b.target_id[c]; a.wave[k] = b.wave[c]; a.igr[k] = b.igr[c]; a.kmax[k] = b.kmax[c];
+      a.periods[k] = b.periods[c]; a.curve_off[k] = b.curve_off[c]; a.synth_off[k] = b.synth_off[c];
+    }
+    swl[1].ncurves = 0;
+  }
+  swl[1].counter_base = swl[0].ncurves;
   for (int t = 0; t < ts.ntargets; ++t)
     if (is_rf(ts.t[t].ref)) { first_rf = t; break; }
   const bool have_rf = first_rf >= 0;
   PrepOut prep = e->prep;
   prep.swd_stride = odd_stride(lmax);   // rows of this batch; buffer is sized for max_layers
-  BH_CUDA(cudaMemsetAsync(e->counters, 0, 2 * sizeof(unsigned long long), st));
+  BH_CUDA(cudaMemsetAsync(e->counters, 0, BH_NUM_COUNTERS * sizeof(unsigned long long), st));
 
   cudaStream_t st_rf = st;
-  if (have_rf && sw.ncurves > 0 && e->concurrent) {
+  if (have_rf && nswd > 0 && e->concurrent) {
     BH_CUDA(cudaEventRecord(e->ev_fork, st));
     BH_CUDA(cudaStreamWaitEvent(e->s_aux, e->ev_fork, 0));
     st_rf = e->s_aux;
   }
 
   for (bool& u : e->pev_used) u = false;
-  if (sw.ncurves > 0) {
+  bool love_forked = false;
+  if (nswd > 0) {
     { KTimer kt(e, BH_K_PREP_SWD, st);
       launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st); }
-    sw.rows = prep.swd_rows; sw.row_stride = prep.swd_stride; sw.nlay = nlay; sw.B = B;
-    sw.curves = e->curves; sw.roots = e->roots; sw.curve_stride = e->curve_stride;
-    sw.tstatus = e->tstatus; sw.counters = e->counters;
-    sw.lcap = lmax;
-    // searches per warp: phase curves S, group curves S_g (two roots per period ->
-    // about twice the serial chain -> more lanes per search for bracket speculation)
+    // models per warp: phase curves S (one chain per model), group curves S_g <= 16
+    // (two chains per model)
     int S = e->searches_per_warp, Sg = e->group_spw;
     if (S == 0) {
       // enough warps to give every SM sub-partition a few (148 SMs x 4 x ~3)
-      const long long nsearch = (long long)B * sw.ncurves;
+      const long long nsearch = (long long)B * nswd;
       S = 32;
       while (S > 1 && nsearch / S < 1776) S >>= 1;
     }
     if (Sg == 0) Sg = S > 1 ? S / 2 : 1;
-    if (Sg > 16) Sg = 16;                 // two chains (lanes) per group search
-    // keep one warp's records within ~16 KB of shared memory
-    while (S > 1 && swd_smem_bytes(lmax, S) > 16 * 1024) S >>= 1;
-    while (Sg > 1 && swd_smem_bytes(lmax, Sg) > 16 * 1024) Sg >>= 1;
-    for (int c = 0; c < sw.ncurves; ++c) sw.spw[c] = sw.igr[c] ? Sg : S;
-    sw.max_spec = e->max_spec;
-    { KTimer kt(e, BH_K_SWD, st); launch_swd(sw, st); }
+    if (Sg > 16) Sg = 16;
+    // keep one warp's records within ~20 KB of shared memory
+    while (S > 1 && swd_smem_bytes(lmax, S) > 20 * 1024) S >>= 1;
+    while (Sg > 1 && swd_smem_bytes(lmax, Sg) > 20 * 1024) Sg >>= 1;
+    if (swl[0].ncurves > 0 && swl[1].ncurves > 0 && e->concurrent) {
+      // Love chains share the SMs with the Rayleigh chains: own stream, forked after
+      // the row preparation and before the Rayleigh launch
+      BH_CUDA(cudaEventRecord(e->ev_fork2, st));
+      BH_CUDA(cudaStreamWaitEvent(e->s_aux2, e->ev_fork2, 0));
+      love_forked = true;
+    }
+    for (int w = 0; w < 2; ++w) {
+      SwdLaunch& sw = swl[w];
+      if (sw.ncurves == 0) continue;
+      sw.rows = prep.swd_rows; sw.row_stride = prep.swd_stride; sw.nlay = nlay; sw.B = B;
+      sw.curves = e->curves; sw.roots = e->roots; sw.curve_stride = e->curve_stride;
+      sw.tstatus = e->tstatus; sw.counters = e->counters;
+      sw.lcap = lmax;
+      for (int c = 0; c < sw.ncurves; ++c) sw.spw[c] = sw.igr[c] ? Sg : S;
+      sw.max_spec = e->max_spec;
+      sw.direct = (e->direct == 2 || (e->direct == 1 && S == 32 && Sg == 16)) ? 1 : 0;
+      cudaStream_t sst = st;
+      if (w == 1 && love_forked) sst = e->s_aux2;
+      bool mixed = false;
+      for (int c = 1; c < sw.ncurves; ++c) mixed |= sw.wave[c] != sw.wave[0];
+      if (mixed && e->rayleigh_sm_pct > 0 && e->nsm > 1 && e->nsm <= 1024) {
+        // dedicate SMs [0, split) to the Rayleigh items, the rest to the Love items
+        long long wr = 0, wl = 0;
+        for (int c = 0; c < sw.ncurves; ++c) (sw.wave[c] == 2 ? wr : wl) += (B + sw.spw[c] - 1) / sw.spw[c];
+        int split = (e->nsm * e->rayleigh_sm_pct / 100) & ~1;      // whole TPCs
+        if (split < 2) split = 2;
+        if (split > e->nsm - 2) split = e->nsm - 2;
+        sw.queue = e->swd_queue; sw.sm_split = split;
+        sw.type_quota[0] = (int)((wr + split - 1) / split);
+        sw.type_quota[1] = (int)((wl + (e->nsm - split) - 1) / (e->nsm - split));
+        BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
+      }
+      { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
+    }
   }
   for (int t = 0; t < ts.ntargets; ++t) {
     const TargetDev& d = ts.t[t];
@@ -378,6 +446,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   if (st_rf != st) {
     BH_CUDA(cudaEventRecord(e->ev_join, st_rf));
     BH_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+  }
+  if (love_forked) {
+    BH_CUDA(cudaEventRecord(e->ev_join2, e->s_aux2));
+    BH_CUDA(cudaStreamWaitEvent(st, e->ev_join2, 0));
   }
   LoglikLaunch ll{};
   ll.ts = ts;
@@ -431,10 +503,9 @@ int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay, cons
 
 int bh_engine_last_counts(bh_engine* e, long long* nsec) {
   if (!e || !nsec) return set_err(BH_ERR_ARG, "null argument");
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[BH_NUM_COUNTERS];
   BH_CUDA(cudaMemcpy(h, e->counters, sizeof(h), cudaMemcpyDeviceToHost));
-  nsec[0] = (long long)h[0];
-  nsec[1] = (long long)h[1];
+  for (int i = 0; i < BH_NUM_COUNTERS; ++i) nsec[i] = (long long)h[i];
   return BH_OK;
 }
 
@@ -505,7 +576,7 @@ int bh_surfdisp96(const float* thkm, const float* vpm, const float* vsm, const f
   sw.rows = s.rows; sw.row_stride = odd_stride(nlayer); sw.nlay = s.nlay; sw.B = 1; sw.ncurves = 1;
   sw.target_id[0] = 0; sw.wave[0] = iwave; sw.igr[0] = igr > 0 ? 1 : 0; sw.kmax[0] = kmax;
   sw.periods[0] = s.periods; sw.curves = s.curve; sw.roots = s.roots; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
-  sw.tstatus = s.tstatus; sw.counters = nullptr; sw.spw[0] = 1; sw.lcap = nlayer; sw.max_spec = 32;
+  sw.tstatus = s.tstatus; sw.counters = nullptr; sw.spw[0] = 1; sw.lcap = nlayer; sw.max_spec = 32; sw.direct = 0;
   launch_swd(sw, s.st);
   int ok = 0;
   std::vector<double> out(kmax);

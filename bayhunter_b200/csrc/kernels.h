@@ -2,6 +2,7 @@
 // translation units.  Not part of the public ABI (see include/bayhunter_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "bh_common.cuh"
 #include "rf_core.cuh"
 #include "swd_core.cuh"
@@ -9,6 +10,23 @@
 namespace bh {
 
 constexpr int kMaxTargets = 8;
+
+// Every kernel of the engine asks for the SAME shared-memory carve-out: an SM
+// only hosts CTAs of kernels that agree on its L1/shared split, and the engine
+// relies on the dispersion (Rayleigh, Love) and receiver-function kernels of one
+// evaluation sharing the SMs from three streams.
+inline int bh_carveout_pct() {
+  static int pct = -2;
+  if (pct == -2) {
+    const char* e = getenv("BH_CARVEOUT");     // developer override; -1 = driver default
+    pct = e ? atoi(e) : 100;                   // all of it shared: the kernels keep no local memory
+  }
+  return pct;
+}
+template <class K>
+inline void bh_set_carveout(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, bh_carveout_pct());
+}
 
 // ---- per-target device-side description --------------------------------
 struct TargetDev {
@@ -70,10 +88,19 @@ struct SwdLaunch {
   int curve_stride;
   int curve_off[kMaxTargets];
   int* tstatus;                 // [B][kMaxTargets] 1 ok / 0 failed
-  unsigned long long* counters; // [2] consumed / evaluated secular values
+  unsigned long long* counters; // [2 + 2*kMaxTargets] consumed / evaluated secular values; per curve sum / max of warp rounds
   int spw[kMaxTargets];         // searches per warp of each curve, 1..32
   int warp_begin[kMaxTargets + 1];  // filled by launch_swd: first warp (= CTA) of each curve
   int max_spec;                 // speculative bracket candidates per search per round
+  int counter_base;             // index of this launch's first curve in the per-curve counters
+  // SM partition of a mixed (Rayleigh + Love) launch: CTAs on SMs [0, sm_split) prefer the
+  // Rayleigh work items, the others the Love items, so that an SM's instruction cache holds
+  // one of the two code paths.  queue: [0..1] next item per type, [2..2+nsm) CTAs started per SM.
+  int* queue;                   // zeroed before the launch; null = static blockIdx mapping
+  int sm_split;
+  int type_quota[2];            // CTAs per SM that take the SM's own type before preferring the other
+  int type_begin[3];            // filled by launch_swd: first warp of Rayleigh items, Love items, end
+  int direct;                   // 1: no speculation (swd_kernel<true>), needs spw = 32 / 16
 };
 void launch_swd(SwdLaunch& p, cudaStream_t st);
 size_t swd_smem_bytes(int lcap, int S);

@@ -162,6 +162,8 @@ void launch_loglik(const LoglikLaunch& p, cudaStream_t st) {
     configured = smem;
   }
   const int blocks = (p.B + kWarps - 1) / kWarps;
+  static bool carved = false;
+  if (!carved) { bh_set_carveout(loglik_kernel); carved = true; }
   loglik_kernel<<<blocks, kWarps * 32, smem, st>>>(p);
 }
 

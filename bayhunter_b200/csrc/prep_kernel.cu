@@ -125,6 +125,8 @@ void launch_prepare(const double* model, const int* nlay, const double* rho, int
   if (total <= 0) return;
   int threads = 128;
   int blocks = (total + threads - 1) / threads;
+  static bool carved = false;
+  if (!carved) { bh_set_carveout(prepare_kernel); carved = true; }
   prepare_kernel<<<blocks, threads, 0, st>>>(model, nlay, rho, B, lmax, want_swd ? 1 : 0,
                                              want_rf ? 1 : 0, rf_p, rf_nsv, rf_qp, rf_qs, out);
 }
@@ -134,6 +136,8 @@ void launch_prepare_rf_explicit(const double* z, const double* vp, const double*
                                 double p, double nsv, double sigma, PrepOut out, cudaStream_t st) {
   int threads = 128;
   int blocks = (nlay + threads - 1) / threads;
+  static bool carved = false;
+  if (!carved) { bh_set_carveout(prepare_rf_explicit_kernel); carved = true; }
   prepare_rf_explicit_kernel<<<blocks, threads, 0, st>>>(z, vp, vs, rho, qp, qs, nlay, p, nsv,
                                                          sigma, out);
 }

@@ -93,6 +93,8 @@ void launch_rf_spectrum(const RfLaunch& p, cudaStream_t st) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = 148LL * 64;   // grid-stride beyond ~64 CTAs per SM
   if (blocks > cap) blocks = cap;
+  static bool carved = false;
+  if (!carved) { bh_set_carveout(rf_spectrum_kernel); carved = true; }
   rf_spectrum_kernel<<<(int)blocks, threads, 0, st>>>(p);
 }
 
@@ -108,6 +110,8 @@ void launch_rf_synth(const RfLaunch& p, cudaStream_t st) {
     cudaFuncSetAttribute(rf_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
+  static bool carved = false;
+  if (!carved) { bh_set_carveout(rf_synth_kernel); carved = true; }
   rf_synth_kernel<<<p.B, threads, smem, st>>>(p);
 }
 

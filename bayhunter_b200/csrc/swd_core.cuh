@@ -222,8 +222,10 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
 //    saturated secular value at exactly +-1.0 (nevill's sign/ratio tests sit
 //    on that tie, surfdisp96.f:619,628).
 // ---------------------------------------------------------------------------
-#ifndef BH_SWD_PAIR
-#define BH_SWD_PAIR 0
+// 1: layers in groups (4 Love layers / 2 Rayleigh layers side by side, more ILP, more code);
+// 0: one layer at a time (smallest instruction-cache footprint)
+#ifndef BH_SWD_WIDE
+#define BH_SWD_WIDE 0
 #endif
 constexpr int SWD_REC_FIELDS = 6;
 // Rayleigh record fields
@@ -254,74 +256,168 @@ BH_HD void swd_make_rec(int wave, const LayerRow& r, bool halfspace, double* out
 
 struct HalfTerms { double cs, sn_over_r, r_sn, ex, em; };   // cos-like, sin/r, +-r*sin, exponent, exp(-ex)
 
-// `var` for one wave type of one layer (surfdisp96.f:929-968): k = wvno, xk = omega/v,
-// s = (k+xk)|k-xk|, d = thickness.  Returns cosp, w = sinp/ra, x = -+ra*sinp, the
-// evanescent exponent pex (0 unless k > xk) and exp(-pex).
-BH_HD HalfTerms half_terms(double k, double xk, double d) {
-  double s = (k + xk) * fabs(k - xk);
+#define BH_N(...) _Pragma("unroll") for (int i = 0; i < N; ++i) { __VA_ARGS__; }
+
+// `var` for N (wave type, layer) pairs at once (surfdisp96.f:929-968): k = wvno,
+// xk[i] = omega/v_i, s = (k+xk)|k-xk|, d[i] = thickness.  Per pair: cosp,
+// w = sinp/ra, x = -+ra*sinp, the evanescent exponent pex (0 unless k > xk) and
+// exp(-pex).
+//
+// The device version is written "N wide": every step of the rsqrt / exp / sincos
+// sequences is applied to all N pairs before the next step, so that N (and, where
+// exp and sincos run side by side, 2N-3N) independent DFMA chains are adjacent in
+// program order.  One warp then keeps the fp64 pipe busy on its own (measured:
+// DFMA latency 8 cycles, issue 2 cycles -> 4 independent chains saturate it),
+// which matters because the searches leave only 1-3 warps per SM sub-partition.
+template <int N>
+BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* h) {
+#if defined(__CUDA_ARCH__)
+  double s[N], y[N], g[N], hh[N], r[N], p[N], pm[N];
+  bool osc[N];
+  BH_N(s[i] = (k + xk[i]) * fabs(k - xk[i]))
   // grazing (k == xk, reference: cosp = 1, w = d, x = 0): a floored radicand on
   // the oscillatory side gives cos(1e-100 d) = 1, sin(p)/r = d, r sin(p) = 1e-200 d
-  s = (s < 1.0e-200) ? 1.0e-200 : s;
-  const bool osc = k <= xk;
-  double r, ir;
-  fm::sqrt_rsqrt(s, &r, &ir);
-  double p = r * d;
-  double pm = osc ? 0.0 : p;
-  double em = fm::exp_small(-pm);
-  double sn, cs;
-  fm::sincos_cw(p, &sn, &cs);
-  double fac = (pm < 16.0) ? em * em : 0.0;
-  double ch = fma(fac, 0.5, 0.5), sh = fma(fac, -0.5, 0.5);
-  HalfTerms h;
-  h.cs = osc ? cs : ch;
-  double sx = osc ? sn : sh;
-  h.sn_over_r = sx * ir;
-  double rs = r * sx;
-  h.r_sn = osc ? -rs : rs;
-  h.ex = pm;
-  h.em = em;
-  return h;
+  BH_N(s[i] = (s[i] < 1.0e-200) ? 1.0e-200 : s[i]; osc[i] = k <= xk[i])
+  BH_N(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i])))
+  BH_N(g[i] = s[i] * y[i]; hh[i] = 0.5 * y[i])
+  BH_N(r[i] = fma(-g[i], hh[i], 0.5))
+  BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
+  BH_N(r[i] = fma(-g[i], hh[i], 0.5))
+  BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
+  BH_N(r[i] = fma(-g[i], g[i], s[i]))
+  BH_N(g[i] = fma(r[i], hh[i], g[i]); hh[i] = hh[i] + hh[i])      // g = sqrt(s), hh = 1/sqrt(s)
+  BH_N(p[i] = g[i] * d[i]; pm[i] = osc[i] ? 0.0 : p[i])
+  // exp(-pm) and sincos(p), step by step side by side
+  double te[N], ts[N], fe[N], ft[N], re[N], rt[N], z[N], pe[N], ps[N], pc[N];
+  int ne[N], q[N];
+  BH_N(te[i] = fma(-pm[i], BH_K(K_LOG2E), BH_K(K_MAGIC)); ts[i] = fma(p[i], BH_K(K_TWO_OVER_PI), BH_K(K_MAGIC)))
+  BH_N(ne[i] = __double2loint(te[i]); q[i] = __double2loint(ts[i]);
+       fe[i] = te[i] - BH_K(K_MAGIC); ft[i] = ts[i] - BH_K(K_MAGIC))
+  BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_HI), -pm[i]); rt[i] = fma(-ft[i], BH_K(K_PIO2_1), p[i]))
+  BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_LO), re[i]); rt[i] = fma(-ft[i], BH_K(K_PIO2_2), rt[i]))
+  BH_N(pe[i] = fma(BH_K(K_E13), re[i], BH_K(K_E12)); rt[i] = fma(-ft[i], BH_K(K_PIO2_3), rt[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E11)); z[i] = rt[i] * rt[i])
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E10)); ps[i] = fma(BH_K(K_S6), z[i], BH_K(K_S5)); pc[i] = fma(BH_K(K_C6), z[i], BH_K(K_C5)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E9)); ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E8)); ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E7)); ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E6)); ps[i] = fma(ps[i], z[i], BH_K(K_S1)); pc[i] = fma(pc[i], z[i], BH_K(K_C1)))
+  double sn[N], cn[N], hz[N], w1[N];
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E5)); sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); hz[i] = 0.5 * z[i])
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E4)); w1[i] = 1.0 - hz[i]; pc[i] = z[i] * z[i] * pc[i])
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E3)); cn[i] = w1[i] + (((1.0 - w1[i]) - hz[i]) + pc[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], 0.5))
+  BH_N(pe[i] = fma(pe[i], re[i], 1.0))
+  BH_N(pe[i] = fma(pe[i], re[i], 1.0))
+  double em[N], fac[N], ch[N], sh[N];
+  BH_N(em[i] = fm::hi_lo(__double2hiint(pe[i]) + (int)((unsigned)ne[i] << 20), __double2loint(pe[i])))
+  // quadrant fix-up of sin/cos: swap on bit 0, sign flips as XORs on the high words
+  BH_N(double a = (q[i] & 1) ? cn[i] : sn[i]; double b = (q[i] & 1) ? sn[i] : cn[i];
+       sn[i] = fm::hi_lo(__double2hiint(a) ^ ((q[i] & 2) << 30), __double2loint(a));
+       cn[i] = fm::hi_lo(__double2hiint(b) ^ (((q[i] + 1) & 2) << 30), __double2loint(b)))
+  BH_N(fac[i] = (pm[i] < 16.0) ? em[i] * em[i] : 0.0)
+  BH_N(ch[i] = fma(fac[i], 0.5, 0.5); sh[i] = fma(fac[i], -0.5, 0.5))
+  BH_N(h[i].cs = osc[i] ? cn[i] : ch[i]; sh[i] = osc[i] ? sn[i] : sh[i])
+  BH_N(h[i].sn_over_r = sh[i] * hh[i]; double rs = g[i] * sh[i]; h[i].r_sn = osc[i] ? -rs : rs;
+       h[i].ex = pm[i]; h[i].em = em[i])
+#else
+  for (int i = 0; i < N; ++i) {
+    double s = (k + xk[i]) * fabs(k - xk[i]);
+    s = (s < 1.0e-200) ? 1.0e-200 : s;
+    const bool osc = k <= xk[i];
+    double r = sqrt(s), ir = 1.0 / r;
+    double p = r * d[i];
+    double pm = osc ? 0.0 : p;
+    double em = exp(-pm);
+    double sn = sin(p), cs = cos(p);
+    double fac = (pm < 16.0) ? em * em : 0.0;
+    double ch = fac * 0.5 + 0.5, sh = fac * -0.5 + 0.5;
+    h[i].cs = osc ? cs : ch;
+    double sx = osc ? sn : sh;
+    h[i].sn_over_r = sx * ir;
+    double rs = r * sx;
+    h[i].r_sn = osc ? -rs : rs;
+    h[i].ex = pm;
+    h[i].em = em;
+  }
+#endif
+}
+
+// sqrt of N radicands (half-space terms), same rsqrt sequence, floored like above
+template <int N>
+BH_HD void sqrt_n(const double* sIn, double* out) {
+#if defined(__CUDA_ARCH__)
+  double s[N], y[N], g[N], hh[N], r[N];
+  BH_N(s[i] = (sIn[i] < 1.0e-200) ? 1.0e-200 : sIn[i])
+  BH_N(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i])))
+  BH_N(g[i] = s[i] * y[i]; hh[i] = 0.5 * y[i])
+  BH_N(r[i] = fma(-g[i], hh[i], 0.5))
+  BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
+  BH_N(r[i] = fma(-g[i], hh[i], 0.5))
+  BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
+  BH_N(r[i] = fma(-g[i], g[i], s[i]))
+  BH_N(out[i] = (sIn[i] < 1.0e-200) ? 0.0 : fma(r[i], hh[i], g[i]))
+#else
+  for (int i = 0; i < N; ++i) out[i] = sqrt(sIn[i]);
+#endif
 }
 
 // Love: per-layer terms that do not depend on the propagated vector
 struct LoveLayer { double cs, y_over_mu, mu_z; };
 
-BH_HD LoveLayer love_layer(const double* rec, int fs, double wvno, double omega) {
-  HalfTerms q = half_terms(wvno, omega * rec[LR_IB * fs], rec[LR_D * fs]);
-  LoveLayer m;
-  m.cs = q.cs;
-  m.y_over_mu = q.sn_over_r * rec[LR_IMU * fs];
-  m.mu_z = rec[LR_MU * fs] * q.r_sn;
-  return m;
+// N consecutive layers l0, l0-1, ..., l0-N+1 at once (rec points at field 0, layer 0)
+template <int N>
+BH_HD void love_layers_n(const double* rec, int fs, int ls, int l0, double wvno, double omega, LoveLayer* m) {
+  double xk[N], d[N];
+  HalfTerms q[N];
+  BH_N(const double* r = rec + (l0 - i) * ls; xk[i] = omega * r[LR_IB * fs]; d[i] = r[LR_D * fs])
+  half_terms_n<N>(wvno, xk, d, q);
+  BH_N(const double* r = rec + (l0 - i) * ls; m[i].cs = q[i].cs; m[i].y_over_mu = q[i].sn_over_r * r[LR_IMU * fs];
+       m[i].mu_z = r[LR_MU * fs] * q[i].r_sn)
+}
+
+BH_HD void love_apply(const LoveLayer& m, double& e1, double& e2) {
+  double e10 = e1 * m.cs + e2 * m.mu_z;
+  double e20 = e1 * m.y_over_mu + e2 * m.cs;
+  double sc = fm::pow2_rescale2(e10, e20);
+  e1 = e10 * sc;
+  e2 = e20 * sc;
 }
 
 // rec: field f of layer l at rec[f * fs + l * ls]; l = L-1 is the half-space.
-// The layer terms of layer l-1 are computed in the same loop body that applies
-// layer l to the vector: the two are independent, which lets the scheduler hide
-// the serial dot-product / normalisation chain behind the next layer's math.
+// Layers are taken four at a time (their terms are independent of the propagated
+// vector), then applied in turn; every layer ends with the exact power-of-two
+// rescale, and the reference's normalisation e1 / max(|e1|, |e2|) of the top layer
+// is taken once at the end -- the quotient is bit-identical because both operands
+// carry the same power of two.  Uniform counted loops, each code block once
+// (the kernel is sensitive to its instruction-cache footprint).
 BH_HD double secular_love_rec(const double* rec, int fs, int ls, int L, double wvno, double omega) {
   const double* hs = rec + (L - 1) * ls;
   double ib = hs[LR_IB * fs];
   double xkb = omega * ib;
-  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double srb = (wvno + xkb) * fabs(wvno - xkb), rb;
+  sqrt_n<1>(&srb, &rb);
   double e1 = hs[LR_D * fs] * rb;     // rho * rb
   double e2 = ib * ib;
   if (L < 2) return e1;
-  LoveLayer m = love_layer(rec + (L - 2) * ls, fs, wvno, omega);
-  for (int l = L - 2; l >= 1; --l) {
-    LoveLayer mn = love_layer(rec + (l - 1) * ls, fs, wvno, omega);
-    double e10 = e1 * m.cs + e2 * m.mu_z;
-    double e20 = e1 * m.y_over_mu + e2 * m.cs;
-    double sc = fm::pow2_rescale2(e10, e20);
-    e1 = e10 * sc;
-    e2 = e20 * sc;
-    m = mn;
+  int l = L - 2;
+#pragma unroll 1
+  for (int r = BH_SWD_WIDE ? ((L - 1) & 3) : (L - 1); r > 0; --r, --l) {
+    LoveLayer m;
+    love_layers_n<1>(rec, fs, ls, l, wvno, omega, &m);
+    love_apply(m, e1, e2);
   }
-  double e10 = e1 * m.cs + e2 * m.mu_z;
-  double e20 = e1 * m.y_over_mu + e2 * m.cs;
-  double xnor = fm::absmax(e10, e20);
+#if BH_SWD_WIDE
+#pragma unroll 1
+  for (int g = (L - 1) >> 2; g > 0; --g, l -= 4) {     // layers l .. l-3
+    LoveLayer m[4];
+    love_layers_n<4>(rec, fs, ls, l, wvno, omega, m);
+    love_apply(m[0], e1, e2); love_apply(m[1], e1, e2); love_apply(m[2], e1, e2); love_apply(m[3], e1, e2);
+  }
+#endif
+  double xnor = fm::absmax(e1, e2);
   if (xnor < 1.0e-40) xnor = 1.0;
-  return e10 / xnor;                         // IEEE division: exact +-1.0 when saturated
+  return e1 / xnor;                          // IEEE division: exact +-1.0 when saturated
 }
 
 // Rayleigh: the distinct entries of Dunkin's compound matrix of one layer
@@ -329,13 +425,12 @@ struct DunkinLayer {
   double c11, c12, c13, c14, c15, c21, c22, c23, c24, c31, c32, c33, c34, c35, c41, c42, c43, c51, c53;
 };
 
-BH_HD DunkinLayer dunkin_layer(const double* rec, int fs, double wvno, double wvno2, double omega,
-                               double iomega2) {
-  double dpth = rec[RR_D * fs], rho = rec[RR_RHO * fs], rinv = rec[RR_IRHO * fs];
+// var's products + dnka (:969-983, :1032-1067) from the P and S terms of a layer
+BH_HD DunkinLayer dunkin_from_terms(const double* rec, int fs, const HalfTerms& P, const HalfTerms& S,
+                                    double wvno2, double iomega2) {
+  double rho = rec[RR_RHO * fs], rinv = rec[RR_IRHO * fs];
   double gammk = rec[RR_TB2 * fs] * iomega2;          // 2 (b/omega)^2
   double gam = gammk * wvno2;
-  HalfTerms P = half_terms(wvno, omega * rec[RR_IA * fs], dpth);
-  HalfTerms S = half_terms(wvno, omega * rec[RR_IB * fs], dpth);
   double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
   double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
   double exa = P.ex + S.ex;
@@ -370,13 +465,37 @@ BH_HD DunkinLayer dunkin_layer(const double* rec, int fs, double wvno, double wv
   return m;
 }
 
+// NL consecutive layers l0, l0-1, ... at once: 2*NL half-term chains side by side
+template <int NL>
+BH_HD void dunkin_layers_n(const double* rec, int fs, int ls, int l0, double wvno, double wvno2, double omega,
+                           double iomega2, DunkinLayer* m) {
+  constexpr int N = 2 * NL;
+  double xk[N], d[N];
+  HalfTerms h[N];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const double* r = rec + (l0 - j) * ls;
+    xk[2 * j] = omega * r[RR_IA * fs]; xk[2 * j + 1] = omega * r[RR_IB * fs];
+    d[2 * j] = d[2 * j + 1] = r[RR_D * fs];
+  }
+  half_terms_n<N>(wvno, xk, d, h);
+#pragma unroll
+  for (int j = 0; j < NL; ++j)
+    m[j] = dunkin_from_terms(rec + (l0 - j) * ls, fs, h[2 * j], h[2 * j + 1], wvno2, iomega2);
+}
+
 #define BH_DUNKIN_APPLY(m)                                                          \
   double n0 = e0 * m.c11 + e1 * m.c21 + e2 * m.c31 + e3 * m.c41 + e4 * m.c51;      \
   double n1 = e0 * m.c12 + e1 * m.c22 + e2 * m.c32 + e3 * m.c42 + e4 * m.c41;      \
   double n2 = e0 * m.c13 + e1 * m.c23 + e2 * m.c33 + e3 * m.c43 + e4 * m.c53;      \
   double n3 = e0 * m.c14 + e1 * m.c24 + e2 * m.c34 + e3 * m.c22 + e4 * m.c21;      \
   double n4 = e0 * m.c15 + e1 * m.c14 + e2 * m.c35 + e3 * m.c12 + e4 * m.c11;
-
+#define BH_DUNKIN_STEP(m)                                                           \
+  {                                                                                 \
+    BH_DUNKIN_APPLY(m)                                                              \
+    double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);                              \
+    e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;           \
+  }
 BH_HD double secular_rayleigh_rec(const double* rec, int fs, int ls, int L, double wvno, double omga) {
   double omega = (omga < 1.0e-4) ? 1.0e-4 : omga;
   double iomega = fm::rcp(omega);
@@ -387,8 +506,9 @@ BH_HD double secular_rayleigh_rec(const double* rec, int fs, int ls, int L, doub
     const double* hs = rec + (L - 1) * ls;
     double rho1 = hs[RR_RHO * fs];
     double xka = omega * hs[RR_IA * fs], xkb = omega * hs[RR_IB * fs];
-    double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-    double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    double sr[2] = {(wvno + xka) * fabs(wvno - xka), (wvno + xkb) * fabs(wvno - xkb)}, rr[2];
+    sqrt_n<2>(sr, rr);
+    double ra = rr[0], rb = rr[1];
     double gammk = hs[RR_TB2 * fs] * iomega2;
     double gam = gammk * wvno2;
     double gamm1 = gam - 1.0;
@@ -399,43 +519,32 @@ BH_HD double secular_rayleigh_rec(const double* rec, int fs, int ls, int L, doub
     e4 = wvno2 - ra * rb;
   }
   if (L < 2) return e0;
-#if BH_SWD_PAIR
-  // Two layers per iteration: their matrices are independent of each other and
-  // of the propagated vector, so both are formed in one basic block (four
-  // interleaved sqrt/exp/sincos chains for the fp64 pipe), then applied in turn.
+  // Two layers per iteration: their matrices are independent of each other and of
+  // the propagated vector, so their four half-term chains run side by side, then
+  // the two matrices are applied in turn.
+  // n = L-1 finite layers: an odd n starts with the bottom layer alone, then pairs.
+  // Every layer ends with the exact power-of-two rescale; the reference's
+  // normalisation e0 / max|e| of the top layer is taken once at the end (bit-identical
+  // quotient, see secular_love_rec).  Uniform counted loops, each code block once.
   int l = L - 2;
-  for (; l >= 1; l -= 2) {
-    DunkinLayer ma = dunkin_layer(rec + l * ls, fs, wvno, wvno2, omega, iomega2);
-    DunkinLayer mb = dunkin_layer(rec + (l - 1) * ls, fs, wvno, wvno2, omega, iomega2);
-    {
-      BH_DUNKIN_APPLY(ma)
-      double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
-      e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
-    }
-    BH_DUNKIN_APPLY(mb)
-    if (l == 1) {
-      double t1 = fm::absmax(fm::absmax(fm::absmax(n0, n1), fm::absmax(n2, n3)), n4);
-      if (t1 < 1.0e-40) t1 = 1.0;
-      return n0 / t1;                        // IEEE division: exact +-1.0 when saturated
-    }
-    double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
-    e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
+#pragma unroll 1
+  for (int r = BH_SWD_WIDE ? ((L - 1) & 1) : (L - 1); r > 0; --r, --l) {
+    DunkinLayer m;
+    dunkin_layers_n<1>(rec, fs, ls, l, wvno, wvno2, omega, iomega2, &m);
+    BH_DUNKIN_STEP(m)
   }
-  DunkinLayer m = dunkin_layer(rec, fs, wvno, wvno2, omega, iomega2);   // l == 0
-#else
-  DunkinLayer m = dunkin_layer(rec + (L - 2) * ls, fs, wvno, wvno2, omega, iomega2);
-  for (int l = L - 2; l >= 1; --l) {
-    DunkinLayer mn = dunkin_layer(rec + (l - 1) * ls, fs, wvno, wvno2, omega, iomega2);
-    BH_DUNKIN_APPLY(m)
-    double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
-    e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
-    m = mn;
+#if BH_SWD_WIDE
+#pragma unroll 1
+  for (int g = (L - 1) >> 1; g > 0; --g, l -= 2) {     // layers l, l-1
+    DunkinLayer m[2];
+    dunkin_layers_n<2>(rec, fs, ls, l, wvno, wvno2, omega, iomega2, m);
+    BH_DUNKIN_STEP(m[0])
+    BH_DUNKIN_STEP(m[1])
   }
 #endif
-  BH_DUNKIN_APPLY(m)
-  double t1 = fm::absmax(fm::absmax(fm::absmax(n0, n1), fm::absmax(n2, n3)), n4);
+  double t1 = fm::absmax(fm::absmax(fm::absmax(e0, e1), fm::absmax(e2, e3)), e4);
   if (t1 < 1.0e-40) t1 = 1.0;
-  return n0 / t1;                            // IEEE division: exact +-1.0 when saturated
+  return e0 / t1;                            // IEEE division: exact +-1.0 when saturated
 }
 
 BH_HD double secular_rec(int wave, const double* rec, int fs, int ls, int L, double wvno, double omega) {
@@ -524,8 +633,13 @@ struct Search {
   // nevill
   double c3, del3;
   int nev, nctrl, m;
-  double x[11], y[11];
+  // Neville tableau x(1..11), y(1..11) (:571): x(j) = tab[j * ts], y(j) = tab[(11 + j) * ts].
+  // On the device it lives in shared memory, one column per lane (ts = 32), because a
+  // dynamically indexed member would put the whole struct into local memory.
+  double* tab;
+  int ts;
 };
+constexpr int SWD_TAB_ROWS = 22;
 
 // What role A publishes for role B (one per group search; shared memory on the device)
 struct SearchLink {
@@ -585,7 +699,9 @@ BH_HD bool sign_differs(double a, double b) {   // dsign(1,a) != dsign(1,b), +-0
 // Extremal velocities + start value (surfdisp96.f:139-156, 197-217).  Water
 // layers (vs <= 0.01) are outside this engine's scope: vs > 0 is enforced by
 // BayHunter's priors (SingleChain.py:358-363); such a model is reported failed.
-BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int kmax, int role) {
+BH_HD bool search_setup(Search& s, const LayerRow* rows, int stride, int L, int kmax, int role,
+                        double* tab, int ts) {
+  s.tab = tab; s.ts = ts;
   float betmx = -1.e20f, betmn = 1.e20f;
   int jmn = 0;
   bool solid = true;
@@ -734,20 +850,27 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
       s.m = 1;
       return false;
     }
+    double* const x = s.tab;
+    double* const y = s.tab + 11 * s.ts;
+    const int ts = s.ts;
     if (s.nev == 2) {                                                    // :634-643
-      s.x[s.m] = s.c3;
-      s.y[s.m] = s.del3;
+      x[s.m * ts] = s.c3;
+      y[s.m * ts] = s.del3;
     } else {
-      s.x[0] = s.c1; s.y[0] = s.del1;
-      s.x[1] = s.c2; s.y[1] = s.del2;
+      x[0] = s.c1; y[0] = s.del1;
+      x[ts] = s.c2; y[ts] = s.del2;
       s.m = 1;
     }
     bool bad = false;
+    const double ym = y[s.m * ts];
+    double xn = x[s.m * ts];                                             // x(j+1), updated as we go down
     for (int kk = 1; kk <= s.m; ++kk) {                                  // :649-654
       int j = s.m - kk;
-      double denom = s.y[s.m] - s.y[j];
-      if (fabs(denom) < 1.0e-10 * fabs(s.y[s.m])) { bad = true; break; }
-      s.x[j] = fm::div(-s.y[j] * s.x[j + 1] + s.y[s.m] * s.x[j], denom);
+      const double yj = y[j * ts];
+      double denom = ym - yj;
+      if (fabs(denom) < 1.0e-10 * fabs(ym)) { bad = true; break; }
+      xn = fm::div(-yj * xn + ym * x[j * ts], denom);
+      x[j * ts] = xn;
     }
     if (bad) {                                                           // :663-667
       nevill_request_half(s, ST_RF_TOP);
@@ -755,7 +878,7 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
       s.m = 1;
       return false;
     }
-    s.c3 = s.x[0];                                                       // :655-661
+    s.c3 = x[0];                                                         // :655-661
     s.nev = 2;
     s.m = s.m + 1;
     if (s.m > 10) s.m = 10;

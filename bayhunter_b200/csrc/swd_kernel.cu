@@ -17,7 +17,18 @@
 // (swd_core.cuh: swd_make_rec), field-major [field][layer][search] so that the
 // 32 lanes of a round read 32 distinct banks (or broadcast when several lanes
 // speculate for the same search), plus one small mailbox (WarpShared).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "kernels.h"
+
+// resident warps (= CTAs) per SM the register allocation must allow
+#ifndef BH_SWD_MIN_BLOCKS_RAYLEIGH
+#define BH_SWD_MIN_BLOCKS_RAYLEIGH 12
+#endif
+#ifndef BH_SWD_MIN_BLOCKS_LOVE
+#define BH_SWD_MIN_BLOCKS_LOVE 16
+#endif
 
 namespace bh {
 
@@ -35,6 +46,7 @@ struct WarpShared {
   int nlay[32];       // rows of the owner's model (constant per warp)
   int col[32];        // record column (model slot) of the owner
   int owner_at[32];   // owner lane of the candidate run that starts at this lane
+  double tab[SWD_TAB_ROWS * 32];   // Neville tableaus, one column per lane
 };
 
 __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
@@ -46,17 +58,44 @@ __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(32)
+// kDirect: every chain evaluates only its own next candidate (no speculation, no
+// dealing, no mailbox traffic) -- the mode for large batches, where all 32 lanes
+// of a warp own a chain anyway.  Otherwise spare lanes are dealt to the chains
+// that are walking a bracket (small batches, the single-model shims).
+// kWave: 1 Love, 2 Rayleigh -- one instantiation per wave type, so that the Love
+// chains do not pay for the Rayleigh code's registers; the two are launched on
+// different streams and share the SMs.
+template <bool kDirect, int kWave>
+__global__ void __launch_bounds__(32, kWave == 1 ? BH_SWD_MIN_BLOCKS_LOVE : BH_SWD_MIN_BLOCKS_RAYLEIGH)
 swd_kernel(SwdLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
-  const int gw = blockIdx.x;                          // global warp id
+  int gw = blockIdx.x;                                // work item = global warp id
+  if (kWave == 0 && p.queue) {
+    // mixed launch: claim an item of the wave type this SM is dedicated to
+    int item = -1;
+    if (lane == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      int t = ((int)smid < p.sm_split) ? 0 : 1;
+      if (atomicAdd(&p.queue[2 + smid], 1) >= p.type_quota[t]) t ^= 1;
+      int i = atomicAdd(&p.queue[t], 1);
+      if (p.type_begin[t] + i >= p.type_begin[t + 1]) {
+        t ^= 1;
+        i = atomicAdd(&p.queue[t], 1);
+      }
+      if (p.type_begin[t] + i < p.type_begin[t + 1]) item = p.type_begin[t] + i;
+    }
+    gw = __shfl_sync(0xffffffffu, item, 0);
+    if (gw < 0) return;
+  }
   int curve = 0;
   while (curve + 1 < p.ncurves && gw >= p.warp_begin[curve + 1]) ++curve;
   const int S = p.spw[curve];                         // models per warp (<= 16 for group curves)
   const int b0 = (gw - p.warp_begin[curve]) * S;      // first model of this warp
   const int nsearch = min(S, p.B - b0);
-  const int wave = p.wave[curve], igr = p.igr[curve], kmax = p.kmax[curve];
+  const int wave = kWave ? kWave : p.wave[curve];     // kWave == 0: mixed launch, wave per curve
+  const int igr = p.igr[curve], kmax = p.kmax[curve];
   const double* __restrict__ periods = p.periods[curve];
   const int tid = p.target_id[curve];
   const int stride = p.row_stride;                    // rows per model in p.rows
@@ -89,7 +128,7 @@ swd_kernel(SwdLaunch p) {
   if (owner) {
     myL = p.nlay[b0 + sidx];
     if (myL > lcap) myL = lcap;
-    if (search_setup(s, p.rows + (size_t)(b0 + sidx) * stride, 1, myL, kmax, role)) {
+    if (search_setup(s, p.rows + (size_t)(b0 + sidx) * stride, 1, myL, kmax, role, ws->tab + lane, 32)) {
       if (role == 0) search_begin_a(s, ctx);
     } else if (role == 0 && ctx.link) {
       ctx.link->a_failed = 1;
@@ -115,9 +154,30 @@ swd_kernel(SwdLaunch p) {
   __syncwarp();
 
   unsigned long long consumed = 0, evaluated = 0;
+  unsigned rounds = 0;
   const int max_spec = p.max_spec;
   const double dc = fabs((double)0.005f);
 
+  if (kDirect) {
+    const double* __restrict__ myrec = rec + sidx;
+    for (;;) {
+      if (role) search_poll_b(s, ctx);
+      const bool run = s.stage < ST_WAIT;
+      if (!__any_sync(0xffffffffu, run)) {
+        if (!__any_sync(0xffffffffu, s.stage == ST_WAIT)) break;
+        __syncwarp();
+        continue;
+      }
+      ++rounds;
+      if (run) {
+        const double c = candidate_from(s.stage, search_pending_c(s), s.idir, s.clow, dc, 0);
+        const double v = secular_rec(wave, myrec, fs, S, myL, fm::div(s.omega, c), s.omega);
+        consumed += search_consume(s, &v, 1, ctx);
+      }
+      __syncwarp();    // orders role A's published roots before role B's next poll
+    }
+    evaluated = consumed;
+  } else
   for (;;) {
     // ---- phase A: owners publish, warp deals lanes ----
     if (role) search_poll_b(s, ctx);
@@ -130,6 +190,7 @@ swd_kernel(SwdLaunch p) {
       __syncwarp();
       continue;
     }
+    ++rounds;
     unsigned bracket = __ballot_sync(0xffffffffu, want > 1);
     int nact = __popc(active), nbr = __popc(bracket);
     int extra = 32 - nact;
@@ -200,6 +261,8 @@ swd_kernel(SwdLaunch p) {
   if (lane == 0 && p.counters) {
     atomicAdd(&p.counters[0], consumed);
     atomicAdd(&p.counters[1], evaluated);
+    atomicAdd(&p.counters[2 + 2 * (p.counter_base + curve)], (unsigned long long)rounds);
+    atomicMax(&p.counters[3 + 2 * (p.counter_base + curve)], (unsigned long long)rounds);
   }
 }
 
@@ -209,6 +272,30 @@ size_t swd_smem_bytes(int lcap, int S) {
   return (size_t)SWD_REC_FIELDS * lcap * S * sizeof(double) + sizeof(WarpShared);
 }
 
+template <bool kDirect, int kWave>
+static void launch_one(const SwdLaunch& p, int warps, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  static bool carved = false;
+  if (!carved) { bh_set_carveout(swd_kernel<kDirect, kWave>); carved = true; }
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(swd_kernel<kDirect, kWave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  static bool reported = false;
+  if (!reported && getenv("BH_DEBUG")) {
+    reported = true;
+    int nb = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, swd_kernel<kDirect, kWave>, 32, smem);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, swd_kernel<kDirect, kWave>);
+    fprintf(stderr, "[bh] swd_kernel<%d,%d>: %d warps, smem %zu B, regs %d, local %zu B, carveout %d, max resident CTAs/SM %d\n",
+            (int)kDirect, kWave, warps, smem, fa.numRegs, fa.localSizeBytes, fa.preferredShmemCarveout, nb);
+  }
+  swd_kernel<kDirect, kWave><<<warps, 32, smem, st>>>(p);
+}
+
+// Curves of one wave type run the specialised instantiation; a mixed set of curves
+// runs the generic one (one launch, Rayleigh and Love warps side by side).
 void launch_swd(SwdLaunch& p, cudaStream_t st) {
   if (p.ncurves <= 0 || p.B <= 0) return;
   int warps = 0, smax = 1;
@@ -218,13 +305,23 @@ void launch_swd(SwdLaunch& p, cudaStream_t st) {
     if (p.spw[c] > smax) smax = p.spw[c];
   }
   p.warp_begin[p.ncurves] = warps;
-  const size_t smem = swd_smem_bytes(p.lcap, smax);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(swd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+  {
+    int c = 0;
+    while (c < p.ncurves && p.wave[c] == 2) ++c;      // Rayleigh curves come first
+    p.type_begin[0] = 0; p.type_begin[1] = p.warp_begin[c]; p.type_begin[2] = warps;
   }
-  swd_kernel<<<warps, 32, smem, st>>>(p);
+  const size_t smem = swd_smem_bytes(p.lcap, smax);
+  int kind = p.wave[0];
+  for (int c = 1; c < p.ncurves; ++c) if (p.wave[c] != kind) kind = 0;
+  if (p.direct) {
+    if (kind == 1) launch_one<true, 1>(p, warps, smem, st);
+    else if (kind == 2) launch_one<true, 2>(p, warps, smem, st);
+    else launch_one<true, 0>(p, warps, smem, st);
+  } else {
+    if (kind == 1) launch_one<false, 1>(p, warps, smem, st);
+    else if (kind == 2) launch_one<false, 2>(p, warps, smem, st);
+    else launch_one<false, 0>(p, warps, smem, st);
+  }
 }
 
 }  // namespace bh

@@ -110,9 +110,15 @@ class Engine(object):
             _lib.check(self._lib.bh_engine_set(self._h, k.encode(), int(v)))
 
     def last_counts(self):
-        buf = (ctypes.c_longlong * 2)()
+        """(consumed, evaluated) secular-function values of the last eval."""
+        c = self.last_counters()
+        return c[0], c[1]
+
+    def last_counters(self):
+        """All work counters (include/bayhunter_b200.h: bh_engine_last_counts)."""
+        buf = (ctypes.c_longlong * _lib.NUM_COUNTERS)()
         _lib.check(self._lib.bh_engine_last_counts(self._h, buf))
-        return int(buf[0]), int(buf[1])
+        return [int(v) for v in buf]
 
     def last_kernel_ms(self):
         """{kernel name: device ms} of the last eval (needs set(profile=1))."""

@@ -108,6 +108,11 @@ int bh_engine_synth_stride(const bh_engine* e);
 /* Tunables (call before eval; all have working defaults).
  *   key "swd_searches_per_warp"  1..32   phase-velocity curves (default chosen from the batch size)
  *   key "swd_group_searches_per_warp" 1..32  group-velocity curves (default: half of the above)
+ *   key "swd_direct"             0/1/2   chains evaluate only their own candidate: never (default) /
+ *                                        when warps are full of chains / always
+ *   key "swd_rayleigh_sm_pct"    0..100  one launch: share of the SMs whose CTAs take the Rayleigh work
+ *                                        items (the rest take Love; 0 = no partition, the default)
+ *   key "swd_split_waves"        0/1     Rayleigh and Love curves in one launch (default) or two
  *   key "swd_max_spec"           1..32   speculative bracket candidates per search
  *   key "concurrent"             0/1     run SWD and RF kernels on forked streams
  *   key "profile"                0/1     record per-kernel event timings */
@@ -146,11 +151,16 @@ int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay,
 #define BH_K_RF_SPECTRUM 3
 #define BH_K_RF_SYNTH 4
 #define BH_K_LOGLIK 5
-#define BH_NUM_KERNELS 6
+#define BH_K_SWD_LOVE 6   /* BH_K_SWD is the Rayleigh launch */
+#define BH_NUM_KERNELS 7
 int bh_engine_last_kernel_ms(bh_engine* e, float* ms);
 
-/* Secular-function evaluations issued by the last eval: nsec[0] = consumed by
- * the searches, nsec[1] = evaluated (>= nsec[0] with speculation). Host ints. */
+/* Work counters of the last eval, nsec[BH_NUM_COUNTERS] host ints:
+ *   [0] secular-function values consumed by the searches, [1] evaluated (>= [0]
+ *   with speculation); then per dispersion curve c (in launch order: Rayleigh
+ *   group, Rayleigh phase, Love group, Love phase): [2+2c] sum over warps of the
+ *   evaluation rounds, [3+2c] the maximum over warps. */
+#define BH_NUM_COUNTERS (2 + 2 * BH_MAX_TARGETS)
 int bh_engine_last_counts(bh_engine* e, long long* nsec);
 
 /*

@@ -39,9 +39,10 @@ int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, c
   SearchCtx ctx; ctx.omA = omA; ctx.omB = omB; ctx.ra = ra; ctx.rb = rb; ctx.link = igr > 0 ? &link : nullptr;
   Search m[2];
   long long consumed = 0, evaluated = 0;
-  if (search_setup(m[0], rows.data(), 1, nlayer, kmax, 0)) search_begin_a(m[0], ctx);
+  double tab[2][SWD_TAB_ROWS];
+  if (search_setup(m[0], rows.data(), 1, nlayer, kmax, 0, tab[0], 1)) search_begin_a(m[0], ctx);
   else link.a_failed = 1;
-  if (igr > 0) search_setup(m[1], rows.data(), 1, nlayer, kmax, 1);
+  if (igr > 0) search_setup(m[1], rows.data(), 1, nlayer, kmax, 1, tab[1], 1);
   else m[1].stage = ST_DONE;
   uint32_t rng = seed;
   double del[2][32];

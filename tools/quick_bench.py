@@ -50,13 +50,14 @@ def run(cfg, B, settings, reps=3):
             if best is None or ms < best[0]:
                 best = (ms, k)
         cons, ev = eng.last_counts()
+        ctr = eng.last_counters() if hasattr(eng, 'last_counters') else []
         logL = out[0].cpu().numpy()
         if ref is None:
             ref = logL
         same = bool(np.array_equal(ref, logL, equal_nan=True))
         print(json.dumps(dict(cfg=cfg, B=B, **st, total_ms=round(best[0], 3),
                               evals_per_s=round(B / best[0] * 1e3), kernels={a: round(b, 3) for a, b in best[1].items()},
-                              consumed=cons, evaluated=ev, valid=float(out[2].float().mean()),
+                              consumed=cons, evaluated=ev, rounds=ctr[2:10], valid=float(out[2].float().mean()),
                               logL_sum=float(np.nansum(logL)), same_as_first=same)), flush=True)
 
 
