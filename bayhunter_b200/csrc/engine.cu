@@ -374,19 +374,31 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     { KTimer kt(e, BH_K_PREP_SWD, st);
       launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st); }
     // models per warp: phase curves S (one chain per model), group curves S_g <= 16
-    // (two chains per model)
+    // (two chains per model).  Fewer models per warp = more spare lanes for bracket
+    // speculation = fewer rounds, but more warps to issue.  Measured on B200
+    // (profiles/r01_swd_sweep.txt): ~2048 warps are best when there are enough chains
+    // to fill them (>= 32768), ~1024 warps below that.
     int S = e->searches_per_warp, Sg = e->group_spw;
     if (S == 0) {
-      // enough warps to give every SM sub-partition a few (148 SMs x 4 x ~3)
-      const long long nsearch = (long long)B * nswd;
-      S = 32;
-      while (S > 1 && nsearch / S < 1776) S >>= 1;
+      long long nph = 0, ngr = 0;
+      for (int w = 0; w < 2; ++w)
+        for (int c = 0; c < swl[w].ncurves; ++c) (swl[w].igr[c] ? ngr : nph) += 1;
+      const long long chains = (long long)B * (nph + 2 * ngr);
+      const long long target = chains >= 32768 ? 2048 : 1024;
+      static const int cand[][2] = {{32, 16}, {16, 16}, {16, 8}, {8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {2, 1}, {1, 1}};
+      int pick = 9;
+      for (int i = 0; i < 10; ++i) {
+        const long long warps = nph * ((B + cand[i][0] - 1) / cand[i][0]) + ngr * ((B + cand[i][1] - 1) / cand[i][1]);
+        if (warps >= target) { pick = i; break; }
+      }
+      S = cand[pick][0];
+      if (Sg == 0) Sg = cand[pick][1];
     }
-    if (Sg == 0) Sg = S > 1 ? S / 2 : 1;
+    if (Sg == 0) Sg = S > 16 ? 16 : S;
     if (Sg > 16) Sg = 16;
-    // keep one warp's records within ~20 KB of shared memory
-    while (S > 1 && swd_smem_bytes(lmax, S) > 20 * 1024) S >>= 1;
-    while (Sg > 1 && swd_smem_bytes(lmax, Sg) > 20 * 1024) Sg >>= 1;
+    // keep one warp's records + mailbox within ~24 KB of shared memory
+    while (S > 1 && swd_smem_bytes(lmax, S) > 24 * 1024) S >>= 1;
+    while (Sg > 1 && swd_smem_bytes(lmax, Sg) > 24 * 1024) Sg >>= 1;
     if (swl[0].ncurves > 0 && swl[1].ncurves > 0 && e->concurrent) {
       // Love chains share the SMs with the Rayleigh chains: own stream, forked after
       // the row preparation and before the Rayleigh launch

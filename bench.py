@@ -225,7 +225,7 @@ def cfg_description(cfg, B, c):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="joint5", choices=["swd2", "joint5", "transd3"])
@@ -371,10 +371,11 @@ def main():
         kmean = {k: float(np.mean(v)) for k, v in kernel_ms.items()}
         dom = max(kmean, key=kmean.get)
         nbytes, flops = algorithmic_model(c, nlay, counts[0] / K)
-        # bytes/flops of the dominant kernel alone: SWD reads the REAL*4 rows and writes the curves
-        if dom == "swd":
+        # bytes/flops of the dominant kernel alone: the dispersion kernel reads the REAL*4 rows
+        # (16 B per layer row) and writes the two root tables and the curves
+        if dom in ("swd", "swd_love"):
             nsw = sum(1 for r in c["refs"] if r not in ("prf", "srf"))
-            dom_bytes = float(np.sum(16.0 * nlay)) * 1.0 + 8.0 * nsw * len(c["periods"]) * B
+            dom_bytes = float(np.sum(16.0 * nlay)) + 3 * 8.0 * nsw * len(c["periods"]) * B
             nr = sum(1 for r in c["refs"] if r.startswith("r") and r not in ("prf", "srf"))
             Lm = float(nlay.mean())
             dom_flops = counts[0] / K * (nr * (175.0 * (Lm - 1) + 30.0) + (nsw - nr) * (28.0 * (Lm - 1) + 10.0)) / nsw
@@ -382,6 +383,12 @@ def main():
             dom_bytes, dom_flops = nbytes, flops
         dom_s = kmean[dom] * 1e-3
         fp64_peak = 148 * 64 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12   # DFMA/clk/SM * 2 flop
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(cfg, {}).get(dom + "_kernel")
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,14 +398,16 @@ def main():
                        "valid_fraction": valid_frac, "parallelism": "chains sharded, dp%d" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "bh_engine_eval_host (pinned host buffers)", "matches_device_path": same},
-            "gpu_launches": 6 * K if c["rf"] is not None else 3 * K,
+            "gpu_launches": (6 if c["rf"] is not None else 3) * K,
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": dom_bytes / dom_s / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": dom_bytes,
                          "peak_source": peak_src,
                          "note": "fp64-compute-bound path: see 'fp64' for the binding roofline"},
             "fp64": {"kernel": dom + "_kernel", "achieved_tflops": dom_flops / dom_s / 1e12,
                      "peak_tflops": fp64_peak, "frac": dom_flops / dom_s / 1e12 / fp64_peak,
-                     "peak_source": "148 SM x 64 DFMA/clk x 2 x sm_max_mhz (nominal; not in MEASURED_PEAKS.json)",
+                     "peak_source": "148 SM x 64 DFMA/clk x 2 x sm_max_mhz; DFMA issue rate measured (tools/micro/fp64_latency.cu: "
+                                    "1 warp-DFMA per 2 cycles per sub-partition), clock nominal",
                      "step_flops": flops, "step_tflops": flops / (total_ms / K * 1e-3) / 1e12,
                      "secular_evals_per_step": counts[0] / K, "secular_evaluated_per_step": counts[1] / K},
             "kernel_ms": kmean,
