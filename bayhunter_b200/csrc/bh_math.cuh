@@ -57,6 +57,21 @@ static __constant__ double kTab[K_COUNT] = {
 #define BH_K(i) (::bh::fm::kTab[::bh::fm::i])
 #endif
 
+// The highest-order polynomial coefficients only need ~20 mantissa bits (their terms are
+// < 1e-11 of the result), so they are written as doubles whose low word is zero: ptxas
+// encodes those as 32-bit immediates of the DFMA, which keeps the table short enough
+// for the remaining constants to stay in uniform registers (with all 33 constants the
+// dispersion kernel spilled and refilled ~16 uniform registers per layer).
+#if defined(__CUDA_ARCH__)
+#define BH_KHI(hi) __hiloint2double((int)(hi), 0)
+#define BH_K_E13 BH_KHI(0x3de61246)   /* 1/13! (1 - 5e-8) */
+#define BH_K_E12 BH_KHI(0x3e21eed9)
+#define BH_K_E11 BH_KHI(0x3e5ae645)
+#define BH_K_E10 BH_KHI(0x3e927e50)
+#define BH_K_S6 BH_KHI(0x3de5d93a)
+#define BH_K_C6 BH_KHI(0xbda8faea)
+#endif
+
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ double hi_lo(int hi, int lo) { return __hiloint2double(hi, lo); }
 #endif
@@ -118,10 +133,10 @@ BH_HD double exp_small(double x) {
   double fn = t - BH_K(K_MAGIC);
   double r = fma(-fn, BH_K(K_LN2_HI), x);
   r = fma(-fn, BH_K(K_LN2_LO), r);                       // |r| <= 0.3466
-  double p = BH_K(K_E13);
-  p = fma(p, r, BH_K(K_E12));
-  p = fma(p, r, BH_K(K_E11));
-  p = fma(p, r, BH_K(K_E10));
+  double p = BH_K_E13;
+  p = fma(p, r, BH_K_E12);
+  p = fma(p, r, BH_K_E11);
+  p = fma(p, r, BH_K_E10);
   p = fma(p, r, BH_K(K_E9));
   p = fma(p, r, BH_K(K_E8));
   p = fma(p, r, BH_K(K_E7));
@@ -149,14 +164,14 @@ BH_HD void sincos_cw(double x, double* sn, double* cs) {
   r = fma(-fn, BH_K(K_PIO2_2), r);
   r = fma(-fn, BH_K(K_PIO2_3), r);
   double z = r * r;
-  double ps = BH_K(K_S6);
+  double ps = BH_K_S6;
   ps = fma(ps, z, BH_K(K_S5));
   ps = fma(ps, z, BH_K(K_S4));
   ps = fma(ps, z, BH_K(K_S3));
   ps = fma(ps, z, BH_K(K_S2));
   ps = fma(ps, z, BH_K(K_S1));
   double s = fma(r * z, ps, r);
-  double pc = BH_K(K_C6);
+  double pc = BH_K_C6;
   pc = fma(pc, z, BH_K(K_C5));
   pc = fma(pc, z, BH_K(K_C4));
   pc = fma(pc, z, BH_K(K_C3));

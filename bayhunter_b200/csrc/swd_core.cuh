@@ -295,9 +295,9 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
        fe[i] = te[i] - BH_K(K_MAGIC); ft[i] = ts[i] - BH_K(K_MAGIC))
   BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_HI), -pm[i]); rt[i] = fma(-ft[i], BH_K(K_PIO2_1), p[i]))
   BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_LO), re[i]); rt[i] = fma(-ft[i], BH_K(K_PIO2_2), rt[i]))
-  BH_N(pe[i] = fma(BH_K(K_E13), re[i], BH_K(K_E12)); rt[i] = fma(-ft[i], BH_K(K_PIO2_3), rt[i]))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E11)); z[i] = rt[i] * rt[i])
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E10)); ps[i] = fma(BH_K(K_S6), z[i], BH_K(K_S5)); pc[i] = fma(BH_K(K_C6), z[i], BH_K(K_C5)))
+  BH_N(pe[i] = fma(BH_K_E13, re[i], BH_K_E12); rt[i] = fma(-ft[i], BH_K(K_PIO2_3), rt[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E11); z[i] = rt[i] * rt[i])
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E10); ps[i] = fma(BH_K_S6, z[i], BH_K(K_S5)); pc[i] = fma(BH_K_C6, z[i], BH_K(K_C5)))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E9)); ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4)))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E8)); ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3)))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E7)); ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2)))
