@@ -70,21 +70,6 @@ def test_rf_restatement_matches_compiled_reference_on_random_models(oracle):
             assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
 
 
-def test_golden_random_vectors(oracle, golden_dir):
-    """Vectors generated HERE from the compiled reference rfmini + the reference's own
-    Targets.py (tests/golden/make_golden.py); they travel to the GPU box."""
-    import os
-    path = os.path.join(golden_dir, "golden_random.npz")
-    if not os.path.exists(path):
-        pytest.skip("golden_random.npz not generated")
-    g = np.load(path)
-    for i in range(g["rf_rows"].shape[0]):
-        n = int(g["rf_nlay"][i])
-        vs = g["rf_rows"][i, :n, 0]; vp = vs * g["rf_rows"][i, :n, 1]; h = g["rf_rows"][i, :n, 3]
-        _, y = oracle.recfunc(h, vp, vs, vp * 0.32 + 0.77, g["rf_x"], wtype="P", use_reference=False)
-        assert np.abs(y - g["rf_y"][i]).max() <= 1e-12 * np.abs(g["rf_y"][i]).max()
-
-
 def test_likelihood_closed_forms_match_dense(oracle):
     """The device kernels use closed forms of d^T C^-1 d; check them against the dense
     matrices of the literal restatement (Targets.py:105-148)."""
