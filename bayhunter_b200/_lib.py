@@ -20,7 +20,7 @@ REF_CODES = {"rdispph": 0, "rdispgr": 1, "ldispph": 2, "ldispgr": 3, "prf": 4, "
 COV_EXP, COV_WHITE, COV_WHITE_SCALED, COV_GAUSS = 0, 1, 2, 3
 MAX_TARGETS, MAX_PERIODS, MAX_LAYERS = 8, 60, 100
 NUM_COUNTERS = 2 + 2 * MAX_TARGETS
-KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik", "swd_love")
+KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik", "swd_love", "swd_general")
 
 
 class BhTarget(ctypes.Structure):

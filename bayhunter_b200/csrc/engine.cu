@@ -195,8 +195,9 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
     }
     e->curve_off[t] = coff;
     if (is_swd(s.ref)) {
-      if (s.mode != 1) { rc = set_err(BH_ERR_UNSUPPORTED, "only mode = 1 (fundamental) is implemented"); break; }
-      if (s.flsph != 0) { rc = set_err(BH_ERR_UNSUPPORTED, "only flsph = 0 (flat earth) is implemented"); break; }
+      if (s.mode < 1) { rc = set_err(BH_ERR_ARG, "mode must be >= 1 (1 = fundamental)"); break; }
+      if (s.flsph != 0 && s.flsph != 1) { rc = set_err(BH_ERR_ARG, "flsph must be 0 (flat) or 1 (spherical)"); break; }
+      d.mode = s.mode; d.flsph = s.flsph;
       d.wave = (s.ref == BH_REF_RDISPPH || s.ref == BH_REF_RDISPGR) ? 2 : 1;   // surf96_modsw.py:48-59
       d.igr = (s.ref == BH_REF_RDISPGR || s.ref == BH_REF_LDISPGR) ? 1 : 0;
       if (s.n > BH_MAX_PERIODS) {
@@ -305,6 +306,7 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
     e->direct = value;
   } else if (!strcmp(key, "concurrent")) {
     e->concurrent = value ? 1 : 0;
+
   } else if (!strcmp(key, "profile")) {
     e->profile = value ? 1 : 0;
     if (e->profile && !e->pev[0])
@@ -336,12 +338,25 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     for (int t = 0; t < ts.ntargets; ++t) {
       const TargetDev& d = ts.t[t];
       if (!is_swd(d.ref) || d.wave != want_wave || d.igr != want_igr) continue;
+      if (d.mode != 1 || d.flsph != 0) continue;       // non-default branches: general kernel below
       int c = sw.ncurves++;
       sw.target_id[c] = t; sw.wave[c] = d.wave; sw.igr[c] = d.igr; sw.kmax[c] = d.kmax;
       sw.periods[c] = d.periods; sw.curve_off[c] = e->curve_off[t]; sw.synth_off[c] = d.synth_off;
     }
   }
   const int nswd = swl[0].ncurves + swl[1].ncurves;
+  SwdGeneralLaunch gen{};
+  for (int t = 0; t < ts.ntargets; ++t) {
+    const TargetDev& d = ts.t[t];
+    if (!is_swd(d.ref)) continue;
+    // the packed rows carry vp as vs * vp/vs, so a water layer cannot occur in a batch
+    // (only bh_surfdisp96 sees one); default settings take the fast kernel
+    if (d.mode == 1 && d.flsph == 0) continue;
+    int c = gen.ncurves++;
+    gen.target_id[c] = t; gen.wave[c] = d.wave; gen.igr[c] = d.igr; gen.kmax[c] = d.kmax;
+    gen.mode[c] = d.mode; gen.flsph[c] = d.flsph;
+    gen.periods[c] = d.periods; gen.curve_off[c] = e->curve_off[t];
+  }
   if (!e->split_waves && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
     // one mixed launch: append the Love curves to the Rayleigh launch
     SwdLaunch& a = swl[0];
@@ -370,7 +385,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
 
   for (bool& u : e->pev_used) u = false;
   bool love_forked = false;
-  if (nswd > 0) {
+  if (nswd > 0 || gen.ncurves > 0) {
     { KTimer kt(e, BH_K_PREP_SWD, st);
       launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st); }
     // models per warp: phase curves S (one chain per model), group curves S_g <= 16
@@ -462,6 +477,13 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   if (love_forked) {
     BH_CUDA(cudaEventRecord(e->ev_join2, e->s_aux2));
     BH_CUDA(cudaStreamWaitEvent(st, e->ev_join2, 0));
+  }
+  if (gen.ncurves > 0) {
+    gen.rows = prep.swd_rows; gen.row_stride = prep.swd_stride; gen.lcap = lmax; gen.nlay = nlay; gen.B = B;
+    gen.curves = e->curves; gen.curve_stride = e->curve_stride; gen.tstatus = e->tstatus;
+    gen.counters = e->counters;
+    KTimer kt(e, BH_K_SWD_GENERAL, st);
+    launch_swd_general(gen, st);
   }
   LoglikLaunch ll{};
   ll.ts = ts;
@@ -572,24 +594,37 @@ int bh_surfdisp96(const float* thkm, const float* vpm, const float* vsm, const f
   if (nlayer < 1 || nlayer > BH_MAX_LAYERS || kmax < 1 || kmax > BH_MAX_PERIODS)
     return set_err(BH_ERR_ARG, "nlayer must be 1..100 and kmax 1..60");
   if (iwave != 1 && iwave != 2) return set_err(BH_ERR_ARG, "iwave must be 1 (Love) or 2 (Rayleigh)");
-  if (mode != 1) return set_err(BH_ERR_UNSUPPORTED, "only mode = 1 (fundamental) is implemented");
-  if (iflsph != 0) return set_err(BH_ERR_UNSUPPORTED, "only iflsph = 0 (flat earth) is implemented");
+  if (mode < 1) return set_err(BH_ERR_ARG, "mode must be >= 1");
+  if (iflsph != 0 && iflsph != 1) return set_err(BH_ERR_ARG, "iflsph must be 0 or 1");
   std::lock_guard<std::mutex> lock(g_shim.mu);
   int rc = shim_init();
   if (rc != BH_OK) return rc;
   Shim& s = g_shim;
   std::vector<LayerRow> rows(nlayer);
-  for (int i = 0; i < nlayer; ++i) { rows[i].x = thkm[i]; rows[i].y = vpm[i]; rows[i].z = vsm[i]; rows[i].w = rhom[i]; }
+  bool fluid = false;
+  for (int i = 0; i < nlayer; ++i) {
+    rows[i].x = thkm[i]; rows[i].y = vpm[i]; rows[i].z = vsm[i]; rows[i].w = rhom[i];
+    fluid |= vsm[i] <= 0.01f;
+  }
   BH_CUDA(cudaMemcpyAsync(s.rows, rows.data(), sizeof(LayerRow) * nlayer, cudaMemcpyHostToDevice, s.st));
   BH_CUDA(cudaMemcpyAsync(s.periods, t, sizeof(double) * kmax, cudaMemcpyHostToDevice, s.st));
   BH_CUDA(cudaMemcpyAsync(s.nlay, &nlayer, sizeof(int), cudaMemcpyHostToDevice, s.st));
   BH_CUDA(cudaMemsetAsync(s.curve, 0, sizeof(double) * BH_MAX_PERIODS, s.st));
-  SwdLaunch sw{};
-  sw.rows = s.rows; sw.row_stride = odd_stride(nlayer); sw.nlay = s.nlay; sw.B = 1; sw.ncurves = 1;
-  sw.target_id[0] = 0; sw.wave[0] = iwave; sw.igr[0] = igr > 0 ? 1 : 0; sw.kmax[0] = kmax;
-  sw.periods[0] = s.periods; sw.curves = s.curve; sw.roots = s.roots; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
-  sw.tstatus = s.tstatus; sw.counters = nullptr; sw.spw[0] = 1; sw.lcap = nlayer; sw.max_spec = 32; sw.direct = 0;
-  launch_swd(sw, s.st);
+  if (mode != 1 || iflsph != 0 || fluid) {
+    SwdGeneralLaunch g{};
+    g.rows = s.rows; g.row_stride = odd_stride(nlayer); g.lcap = nlayer; g.nlay = s.nlay; g.B = 1; g.ncurves = 1;
+    g.target_id[0] = 0; g.wave[0] = iwave; g.igr[0] = igr > 0 ? 1 : 0; g.kmax[0] = kmax; g.mode[0] = mode;
+    g.flsph[0] = iflsph; g.periods[0] = s.periods; g.curves = s.curve;
+    g.curve_stride = BH_MAX_PERIODS; g.curve_off[0] = 0; g.tstatus = s.tstatus; g.counters = nullptr;
+    launch_swd_general(g, s.st);
+  } else {
+    SwdLaunch sw{};
+    sw.rows = s.rows; sw.row_stride = odd_stride(nlayer); sw.nlay = s.nlay; sw.B = 1; sw.ncurves = 1;
+    sw.target_id[0] = 0; sw.wave[0] = iwave; sw.igr[0] = igr > 0 ? 1 : 0; sw.kmax[0] = kmax;
+    sw.periods[0] = s.periods; sw.curves = s.curve; sw.roots = s.roots; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
+    sw.tstatus = s.tstatus; sw.counters = nullptr; sw.spw[0] = 1; sw.lcap = nlayer; sw.max_spec = 32; sw.direct = 0;
+    launch_swd(sw, s.st);
+  }
   int ok = 0;
   std::vector<double> out(kmax);
   BH_CUDA(cudaMemcpyAsync(out.data(), s.curve, sizeof(double) * kmax, cudaMemcpyDeviceToHost, s.st));

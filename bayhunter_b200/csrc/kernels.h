@@ -42,6 +42,7 @@ struct TargetDev {
   double log_serr_prod;     // log(prod(serr)) (WHITE_SCALED)
   // SWD
   int wave, igr, kmax;      // kmax = min(n, 60) periods actually searched
+  int mode, flsph;          // SurfDisp.set_modelparams keys (surf96_modsw.py:28-31)
   const double* periods;    // [kmax] device: x, or the 60-point resampling (n > 60)
   // RF
   int nsamp, waveno;
@@ -104,6 +105,26 @@ struct SwdLaunch {
 };
 void launch_swd(SwdLaunch& p, cudaStream_t st);
 size_t swd_smem_bytes(int lcap, int S);
+
+// Non-default SURF96 branches (higher modes, earth flattening, water layer): one thread
+// per (model, curve), see swd_general.cu.
+struct SwdGeneralLaunch {
+  const LayerRow* rows;         // [B][row_stride] REAL*4 rows (d, vp, vs, rho), flat-earth values
+  int row_stride;
+  int lcap;
+  const int* nlay;
+  int B;
+  int ncurves;
+  int target_id[kMaxTargets];
+  int wave[kMaxTargets], igr[kMaxTargets], kmax[kMaxTargets], mode[kMaxTargets], flsph[kMaxTargets];
+  const double* periods[kMaxTargets];
+  double* curves;               // [B][curve_stride]
+  int curve_stride;
+  int curve_off[kMaxTargets];
+  int* tstatus;                 // [B][kMaxTargets]
+  unsigned long long* counters; // [0], [1] += secular evaluations (may be null)
+};
+void launch_swd_general(const SwdGeneralLaunch& p, cudaStream_t st);
 
 // ---- receiver function ----------------------------------------------------
 struct RfLaunch {

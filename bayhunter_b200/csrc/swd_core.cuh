@@ -36,7 +36,10 @@ typedef f4 LayerRow;
 // Love secular function: Haskell 2-vector from the half-space to the surface.
 // rows[l*stride], l = 0..L-1, l = L-1 is the half-space.
 // ---------------------------------------------------------------------------
-BH_HD double secular_love_reforder(const LayerRow* rows, int stride, int L, double wvno, double omega) {
+// ltop = llw - 1: 1 when the top layer is water (surfdisp96.f:134-135), which Love
+// waves simply skip (:730).
+BH_HD double secular_love_reforder(const LayerRow* rows, int stride, int L, double wvno, double omega,
+                                   int ltop = 0) {
   LayerRow hs = rows[(L - 1) * stride];
   double beta1 = (double)hs.z;
   double rho1 = (double)hs.w;
@@ -44,7 +47,7 @@ BH_HD double secular_love_reforder(const LayerRow* rows, int stride, int L, doub
   double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
   double e1 = rho1 * rb;
   double e2 = 1.0 / (beta1 * beta1);
-  for (int l = L - 2; l >= 0; --l) {
+  for (int l = L - 2; l >= ltop; --l) {
     LayerRow r = rows[l * stride];
     double d = (double)r.x;
     beta1 = (double)r.z;
@@ -87,7 +90,9 @@ BH_HD double secular_love_reforder(const LayerRow* rows, int stride, int L, doub
 // from the half-space up; per layer the eigenfunction products of `var` and
 // the compound matrix of `dnka` are formed in registers.
 // ---------------------------------------------------------------------------
-BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, double wvno, double omga) {
+// ltop = 1: the top layer is water and enters through the fluid boundary condition (:850-867).
+BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, double wvno, double omga,
+                                       int ltop = 0) {
   double omega = (omga < 1.0e-4) ? 1.0e-4 : omga;
   double wvno2 = wvno * wvno;
   double e0, e1, e2, e3, e4;
@@ -107,7 +112,7 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
     e3 = rho1 * rb;
     e4 = wvno2 - ra * rb;
   }
-  for (int l = L - 2; l >= 0; --l) {
+  for (int l = L - 2; l >= ltop; --l) {
     LayerRow r = rows[l * stride];
     double dpth = (double)r.x, a = (double)r.y, b = (double)r.z, rho = (double)r.w;
     double xka = omega / a, xkb = omega / b;
@@ -161,13 +166,12 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
     double gmgm1 = gam * gamm1;
     double gm1sq = gamm1 * gamm1;
     double rho2 = rho * rho;
-    double rinv = 1.0 / rho;
     double a0pq = a0 - cpcq;
     double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
-    double c12 = (wvno2 * cpy - cqx) * rinv;
-    double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * rinv;
-    double c14 = (cpz - wvno2 * cqw) * rinv;
-    double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * (rinv * rinv);
+    double c12 = (wvno2 * cpy - cqx) / rho;
+    double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) / rho;
+    double c14 = (cpz - wvno2 * cqw) / rho;
+    double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) / rho2;
     double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
     double c22 = cpcq;
     double c23 = gammk * cpz - gamm1 * cqw;
@@ -192,8 +196,28 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
     if (t1 < 1.0e-40) t1 = 1.0;
     // e0 is what the caller finally reads: keep the reference's true division so
     // that a saturated component is exactly +-1.0 (see secular_love).
-    double inv = 1.0 / t1;
-    e0 = n0 / t1; e1 = n1 * inv; e2 = n2 * inv; e3 = n3 * inv; e4 = n4 * inv;
+    e0 = n0 / t1; e1 = n1 / t1; e2 = n2 / t1; e3 = n3 / t1; e4 = n4 / t1;
+  }
+  if (ltop != 0) {
+    // water layer on top (:850-867): only the P terms w, cosp of `var` are read
+    LayerRow r = rows[0];
+    double dpth = (double)r.x, rho1 = (double)r.w;
+    double xka = omega / (double)r.y;
+    double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    double p = ra * dpth;
+    double w, cosp;
+    if (wvno < xka) {
+      double sinp;
+      sincos_d(p, &sinp, &cosp);
+      w = sinp / ra;
+    } else if (wvno == xka) {
+      cosp = 1.0; w = dpth;
+    } else {
+      double fac = (p < 16.0) ? exp(-2.0 * p) : 0.0;
+      cosp = (1.0 + fac) * 0.5;
+      w = ((1.0 - fac) * 0.5) / ra;
+    }
+    return cosp * e0 + (-rho1 * w) * e1;
   }
   return e0;
 }

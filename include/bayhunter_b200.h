@@ -77,8 +77,9 @@ typedef struct bh_target {
   const double* corr_inv;  /* [n*n] row-major R^-1 for BH_COV_GAUSS else NULL */
   double logcorr_det;      /* slogdet(R) for BH_COV_GAUSS                     */
   /* SurfDisp.set_modelparams keys (src/surf96_modsw.py:28-31) */
-  int mode;                /* 1 = fundamental (only value supported)          */
-  int flsph;               /* 0 = flat earth (only value supported)           */
+  int mode;                /* number of modes searched, 1 = fundamental; the curve
+                              returned is the highest one (surfdisp96.f:223-311)  */
+  int flsph;               /* 0 = flat earth, 1 = earth-flattening (sphere)    */
   /* RFminiModRF.set_modelparams keys (src/rfmini_modrf.py:26-31) */
   double gauss;            /* Gauss parameter a                               */
   double p;                /* slowness, s/deg                                 */
@@ -152,7 +153,8 @@ int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay,
 #define BH_K_RF_SYNTH 4
 #define BH_K_LOGLIK 5
 #define BH_K_SWD_LOVE 6   /* BH_K_SWD is the Rayleigh launch */
-#define BH_NUM_KERNELS 7
+#define BH_K_SWD_GENERAL 7 /* higher modes / flsph = 1 / water-layer models */
+#define BH_NUM_KERNELS 8
 int bh_engine_last_kernel_ms(bh_engine* e, float* ms);
 
 /* Work counters of the last eval, nsec[BH_NUM_COUNTERS] host ints:
@@ -165,7 +167,8 @@ int bh_engine_last_counts(bh_engine* e, long long* nsec);
 
 /*
  * Single-model shims with the argument meaning of the reference FFI (HOST
- * pointers).  They run the same CUDA kernels with B = 1.
+ * pointers).  They run the same CUDA kernels with B = 1 (mode > 1, iflsph = 1 and
+ * models with a water layer through the general dispersion kernel).
  *
  * bh_surfdisp96: thkm/vpm/vsm/rhom REAL*4 [nlayer]; t, cg fp64 [kmax];
  *   iwave 1 Love / 2 Rayleigh; igr 0 phase / >0 group; *err = 0 ok, 1 no root.

@@ -67,7 +67,7 @@ def ref_rfmini():
 SURFTAGS = {"rdispgr": (2, 1), "ldispgr": (1, 1), "rdispph": (2, 0), "ldispph": (1, 0)}
 
 
-def surfdisp(h, vp, vs, rho, ref, periods, count=None):
+def surfdisp(h, vp, vs, rho, ref, periods, count=None, mode=1, flsph=0):
     """SurfDisp.run_model (src/surf96_modsw.py:84-126): (x, y) or (nan, nan)."""
     periods = np.ascontiguousarray(periods, dtype=np.float64)
     iwave, igr = SURFTAGS[ref]
@@ -78,7 +78,7 @@ def surfdisp(h, vp, vs, rho, ref, periods, count=None):
     cg = np.zeros(pers.size)
     err = ctypes.c_int(0)
     ns = (ctypes.c_long * 2)()
-    lib().surf96_oracle(*[a.ctypes.data_as(_F) for a in arrs], arrs[0].size, 0, iwave, 1, igr,
+    lib().surf96_oracle(*[a.ctypes.data_as(_F) for a in arrs], arrs[0].size, int(flsph), iwave, int(mode), igr,
                         pers.size, pers.ctypes.data_as(_D), cg.ctypes.data_as(_D), ctypes.byref(err), ns)
     if count is not None:
         count[0] += ns[0]
@@ -173,7 +173,8 @@ class OracleTarget(object):
 
     def forward(self, h, vp, vs, rho, count=None):
         if self.ref in SURFTAGS:
-            return surfdisp(h, vp, vs, rho, self.ref, self.x, count=count)
+            return surfdisp(h, vp, vs, rho, self.ref, self.x, count=count,
+                            mode=self.params.get("mode", 1), flsph=self.params.get("flsph", 0))
         kw = {k: v for k, v in self.params.items() if k in ("gauss", "p", "nsv", "use_reference")}
         return recfunc(h, vp, vs, rho, self.x, wtype="SV" if self.ref == "srf" else "P", **kw)
 

@@ -10,6 +10,7 @@
 
 #include "../../bayhunter_b200/csrc/rf_core.cuh"
 #include "../../bayhunter_b200/csrc/swd_core.cuh"
+#include "../../bayhunter_b200/csrc/swd_general_core.cuh"
 
 using namespace bh;
 
@@ -71,6 +72,22 @@ int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, c
   if (ok)
     for (int k = 0; k < kmax; ++k) cg[k] = swd_curve_value(igr, periods[k], ra[k], rb[k]);
   return ok ? 0 : 1;   // err like surfdisp96
+}
+
+// The general dispersion path (higher modes, earth flattening, water layer) exactly as
+// one thread of swd_general_kernel runs it.  Returns err like surfdisp96.
+int swd_sim_general(const float* rows4, int nlayer, int wave, int igr, int kmax, int mode, int flsph,
+                    const double* periods, double* cg, long long* nsec) {
+  std::vector<LayerRow> rows(nlayer);
+  for (int i = 0; i < nlayer; ++i) {
+    rows[i].x = rows4[4 * i]; rows[i].y = rows4[4 * i + 1];
+    rows[i].z = rows4[4 * i + 2]; rows[i].w = rows4[4 * i + 3];
+  }
+  for (int k = 0; k < kmax; ++k) cg[k] = 0.0;
+  unsigned long long n = 0;
+  int err = swd_general_curve(rows.data(), 1, nlayer, wave, igr, kmax, mode, flsph, periods, cg, &n);
+  if (nsec) *nsec = (long long)n;
+  return err;
 }
 
 // Receiver function through rf_core.cuh; same arguments as synrf_cwrap minus fz/fr.

@@ -74,6 +74,98 @@ def test_surfdisp_more_than_60_periods(oracle):
     assert np.array_equal(x, periods) and _rel(y, yo).max() <= 1e-6
 
 
+def _raw_oracle(oracle, h, vp, vs, rho, ref, periods, mode, flsph):
+    import ctypes
+    F = ctypes.POINTER(ctypes.c_float); D = ctypes.POINTER(ctypes.c_double)
+    wave, igr = oracle.SURFTAGS[ref]
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (h, vp, vs, rho)]
+    cg = np.zeros(len(periods)); err = ctypes.c_int(0); ns = (ctypes.c_long * 2)()
+    oracle.lib().surf96_oracle(*[a.ctypes.data_as(F) for a in arrs], len(h), flsph, wave, mode, igr,
+                               len(periods), periods.ctypes.data_as(D), cg.ctypes.data_as(D), ctypes.byref(err), ns)
+    return cg, err.value
+
+
+def test_surfdisp_plugin_modes_sphere_water(oracle):
+    """SurfDisp.set_modelparams(mode=, flsph=) and water-layer models: the general dispersion
+    kernel against the oracle.  Higher modes that do not exist at a period leave 0 there with
+    err = 0 (surfdisp96.f:350-354).  Tolerance: phase 1e-6, group 5e-5 (module docstring)."""
+    from bayhunter_b200 import SurfDisp, synthetic
+    rng = np.random.default_rng(15)
+    periods = np.linspace(1, 40, 24)
+    nwater = nhigher = nzero = 0
+    for it in range(24):
+        k = int(rng.integers(2, 10))
+        h, vs = synthetic.draw_model(rng, k)
+        vp = vs * rng.uniform(1.4, 2.1)
+        rho = vp * 0.32 + 0.77
+        if it % 4 == 1 and k >= 3:
+            h[0] = rng.uniform(0.5, 4.0); vs[0] = 0.0; vp[0] = 1.5; rho[0] = 1.03
+            nwater += 1
+        for ref in ("rdispph", "rdispgr", "ldispph", "ldispgr"):
+            for mode, flsph in ((1, 0), (2, 0), (1, 1), (3, 1)):
+                yo, erro = _raw_oracle(oracle, h, vp, vs, rho, ref, periods, mode, flsph)
+                plug = SurfDisp(periods, ref)
+                plug.set_modelparams(mode=mode, flsph=flsph)
+                x, y = plug.run_model(h, vp, vs, rho)
+                if erro:
+                    assert not isinstance(x, np.ndarray), (it, ref, mode, flsph)
+                    continue
+                assert isinstance(x, np.ndarray), (it, ref, mode, flsph)
+                ok = yo != 0
+                assert np.array_equal(ok, y != 0), (it, ref, mode, flsph)
+                nzero += int((~ok).any()); nhigher += int(mode > 1 and ok.any())
+                if ok.any():
+                    tol = 1e-6 if ref.endswith("ph") else 5e-5
+                    assert _rel(y[ok], yo[ok]).max() <= tol, (it, ref, mode, flsph, _rel(y[ok], yo[ok]).max())
+    assert nwater >= 3 and nhigher > 10 and nzero > 0
+
+
+def test_engine_higher_modes_and_sphere(oracle):
+    """Batched engine with non-default SurfDisp parameters on some targets (general kernel)
+    next to default ones (fast kernel) and an RF target."""
+    from bayhunter_b200 import Engine, TargetSpec, synthetic
+    from oracle import joint_oracle as jo
+    rng = np.random.default_rng(16)
+    periods = np.linspace(1, 30, 16)
+    rf = dict(n=201, dt=0.2, t0=-5.0)
+    x_rf = synthetic.rf_time_axis(rf)
+    setups = [("rdispph", dict(mode=2, flsph=0)), ("rdispgr", dict(mode=1, flsph=1)),
+              ("ldispph", dict(mode=2, flsph=1)), ("rdispph", dict()), ("prf", dict())]
+    specs, otargets = [], []
+    for ref, kw in setups:
+        if ref == "prf":
+            x = x_rf
+            _, y = jo.recfunc(ST3_H, ST3_VP, ST3_VS, ST3_RHO, x)
+        else:
+            x = periods
+            y = 3.6 + rng.normal(0, 0.05, x.size)
+        specs.append(TargetSpec(ref, x, y, cov="exp", **kw))
+        otargets.append(jo.OracleTarget(ref, x, y, cov="exp", **kw))
+    B = 48
+    rows, nlay = synthetic.draw_batch(B, (2, 9), seed=41)
+    noise = synthetic.draw_noise(B, [s.ref for s in specs], seed=42)
+    eng = Engine(specs, B, rows.shape[1])
+    eng.set(profile=1)
+    out = eng.eval_host(rows, nlay, noise, want_synth=True)
+    assert "swd_general" in eng.last_kernel_ms() and "swd" in eng.last_kernel_ms()
+    ref_out = oracle.evaluate_batch(otargets, rows, nlay, noise)
+    assert np.array_equal(out[2], ref_out[2])
+    ok = ref_out[2] == 1
+    o = 0
+    for s in specs:
+        a, b = out[3][ok, o:o + s.n], ref_out[3][ok, o:o + s.n]
+        o += s.n
+        if s.ref == "prf":
+            assert (np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)).max() <= 1e-9
+            continue
+        nz = b != 0
+        assert np.array_equal(nz, a != 0), s.ref
+        tol = 1e-6 if s.ref.endswith("ph") else 5e-5
+        assert _rel(a[nz], b[nz]).max() <= tol, (s.ref, s.params, _rel(a[nz], b[nz]).max())
+    e = _logl_check(out[0], ref_out[0], ok)
+    assert np.median(e) <= 1e-6 and (e <= 1e-5).mean() >= 0.9, (np.median(e), e.max())
+
+
 def test_rf_plugin_random_models(oracle):
     from bayhunter_b200 import RFminiModRF, synthetic
     rng = np.random.default_rng(6)

@@ -50,6 +50,61 @@ def test_search_state_machine_equals_oracle_for_any_speculation(oracle, host_sim
     assert nfail > 0
 
 
+def _sim_general(sim, h, vp, vs, rho, wave, igr, t, mode, flsph):
+    rows = np.ascontiguousarray(np.stack([h, vp, vs, rho], 1), dtype=np.float32)
+    cg = np.zeros(len(t))
+    n = ctypes.c_longlong(0)
+    err = sim.swd_sim_general(rows.ctypes.data_as(F), len(h), wave, igr, len(t), mode, flsph,
+                              t.ctypes.data_as(D), cg.ctypes.data_as(D), ctypes.byref(n))
+    return cg, err, n.value
+
+
+def _oracle_raw(oracle, h, vp, vs, rho, wave, igr, t, mode, flsph):
+    """surf96_oracle with the raw (cg, err) outputs: higher modes that do not exist leave
+    zeros in cg with err = 0 (surfdisp96.f:350-354), which SurfDisp.run_model returns as is."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (h, vp, vs, rho)]
+    cg = np.zeros(len(t))
+    err = ctypes.c_int(0)
+    ns = (ctypes.c_long * 2)()
+    oracle.lib().surf96_oracle(*[a.ctypes.data_as(F) for a in arrs], len(h), flsph, wave, mode, igr,
+                               len(t), t.ctypes.data_as(D), cg.ctypes.data_as(D), ctypes.byref(err), ns)
+    return cg, err.value, ns[0] + ns[1]
+
+
+def test_general_path_modes_sphere_water_equal_oracle(oracle, host_sim_reforder):
+    """swd_general_core.cuh (what one thread of swd_general_kernel runs) against the oracle:
+    fundamental + higher modes, flat / earth-flattened, solid stacks and a water layer on
+    top.  Same candidate sequence (equal evaluation counts) and bit-equal curves, except the
+    Rayleigh density power of the sphere transform (powf vs pow rounded once: <= 1e-7)."""
+    t = np.linspace(1, 40, 30)
+    rng = np.random.default_rng(11)
+    n_zero = n_water = n_hi = 0
+    for it, h, vp, vs, rho in _models(rng, 60, kmax=12):
+        water = it % 4 == 1 and len(h) >= 3
+        if water:
+            h = h.copy(); vp = vp.copy(); vs = vs.copy(); rho = rho.copy()
+            h[0] = rng.uniform(0.5, 4.0); vs[0] = 0.0; vp[0] = 1.5; rho[0] = 1.03
+            n_water += 1
+        for ref, (wave, igr) in oracle.SURFTAGS.items():
+            for mode in (1, 2, 3):
+                for flsph in (0, 1):
+                    yo, erro, no = _oracle_raw(oracle, h, vp, vs, rho, wave, igr, t, mode, flsph)
+                    y, err, n = _sim_general(host_sim_reforder, h, vp, vs, rho, wave, igr, t, mode, flsph)
+                    assert err == erro, (it, ref, mode, flsph)
+                    if err:
+                        continue
+                    if flsph == 1 and wave == 2:
+                        ok = yo != 0
+                        assert np.array_equal(ok, y != 0)
+                        assert np.abs(y[ok] - yo[ok]).max(initial=0) <= 1e-7 * np.abs(yo).max()
+                    else:
+                        assert np.array_equal(y, yo), (it, ref, mode, flsph, water)
+                        assert n == no
+                    n_zero += int((yo == 0).any())
+                    n_hi += int(mode > 1 and (yo != 0).any())
+    assert n_water > 5 and n_zero > 0 and n_hi > 20
+
+
 def test_device_formulation_of_secular_functions(oracle, host_sim):
     """The branch-free / reciprocal formulation the kernels use (libm-backed on the host)
     must give the same curves as the oracle to rounding: phase <= 1e-9, group <= 5e-5,
