@@ -35,6 +35,25 @@ class BhTarget(ctypes.Structure):
     ]
 
 
+class BhSamplerConfig(ctypes.Structure):
+    """struct bh_sampler_config (include/bayhunter_b200.h)."""
+    _fields_ = [
+        ("layers_min", ctypes.c_int), ("layers_max", ctypes.c_int),
+        ("vs_min", ctypes.c_double), ("vs_max", ctypes.c_double),
+        ("z_min", ctypes.c_double), ("z_max", ctypes.c_double),
+        ("vpvs_fixed", ctypes.c_int), ("vpvs_min", ctypes.c_double), ("vpvs_max", ctypes.c_double),
+        ("has_mantle", ctypes.c_int), ("mantle_vs", ctypes.c_double), ("mantle_vpvs", ctypes.c_double),
+        ("noise_fixed", ctypes.c_int * (2 * MAX_TARGETS)),
+        ("noise_min", ctypes.c_double * (2 * MAX_TARGETS)), ("noise_max", ctypes.c_double * (2 * MAX_TARGETS)),
+        ("thickmin", ctypes.c_double),
+        ("has_lvz", ctypes.c_int), ("has_hvz", ctypes.c_int),
+        ("lvz", ctypes.c_double), ("hvz", ctypes.c_double),
+        ("propdist", ctypes.c_double * 5), ("acceptance", ctypes.c_double * 2),
+        ("iter_burnin", ctypes.c_int), ("iter_main", ctypes.c_int), ("max_accepted", ctypes.c_int),
+        ("seed", ctypes.c_ulonglong),
+    ]
+
+
 class BayHunterB200Error(RuntimeError):
     def __init__(self, code, message):
         super().__init__("libbayhunter_b200 error %d: %s" % (code, message))
@@ -60,6 +79,16 @@ SIGNATURES = {
     "bh_surfdisp96": (ctypes.c_int, [c_float_p] * 4 + [ctypes.c_int] * 6 +
                       [c_double_p, c_double_p, c_int_p]),
     "bh_debug_math": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p]),
+    "bh_sampler_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BhSamplerConfig), ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_longlong, ctypes.POINTER(ctypes.c_void_p)]),
+    "bh_sampler_destroy": (None, [ctypes.c_void_p]),
+    "bh_sampler_init": (ctypes.c_int, [ctypes.c_void_p] * 5),
+    "bh_sampler_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bh_sampler_get_state": (ctypes.c_int, [ctypes.c_void_p] * 13),
+    "bh_sampler_get_chains": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6),
+    "bh_sampler_set_state": (ctypes.c_int, [ctypes.c_void_p] * 11),
+    "bh_sampler_get_proposal": (ctypes.c_int, [ctypes.c_void_p] * 10),
+    "bh_sampler_set_forced_draws": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "bh_synrf": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 +
                  [c_double_p] * 9),
 }

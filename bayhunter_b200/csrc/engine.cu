@@ -37,6 +37,13 @@ int set_err(int code, const char* what, cudaError_t ce = cudaSuccess) {
   return code;
 }
 
+}  // namespace
+namespace bh {
+// shared with sampler.cu: record a message for bh_last_error() and hand the code back
+int bh_set_error_message(int code, const char* what) { return set_err(code, what); }
+}  // namespace bh
+namespace {
+
 #define BH_CUDA(call)                                                        \
   do {                                                                       \
     cudaError_t _e = (call);                                                 \

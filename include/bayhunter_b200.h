@@ -184,6 +184,88 @@ int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a,
              const double* qp, const double* qs, double* fz, double* fr,
              double* rf);
 
+/* ------------------------------------------------------------------------
+ * Lock-step chain ensemble: the sampler around the hot path, on the device.
+ *
+ *   bh_sampler_*  <- SingleChain.iterate / run_chain (src/SingleChain.py:511-589,
+ *                    591-612) for B chains at once, and the chain arrays of
+ *                    MCMC_Optimizer._init_shareddata (src/mcmcOptimizer.py:78-128).
+ *
+ * Every chain keeps BayHunter's state (Voronoi nuclei, vp/vs, noise parameters,
+ * proposal widths, accepted/proposed counters, iteration counter) in device
+ * memory; one iteration = propose kernel -> bh_engine_eval -> accept kernel, with
+ * no host round trip.  Random variates come from Philox4x32-10 keyed by
+ * (seed, global chain index, iteration): a chain's trajectory does not depend on
+ * the batch it runs in or on the GPU count.
+ * ------------------------------------------------------------------------ */
+typedef struct bh_sampler_config {
+  /* priors (src/defaults/defaults.ini [modelpriors]) */
+  int layers_min, layers_max;          /* priors['layers']; models hold up to layers_max + 1 nuclei */
+  double vs_min, vs_max;               /* priors['vs'] */
+  double z_min, z_max;                 /* priors['z'] */
+  int vpvs_fixed;                      /* priors['vpvs'] given as a float: never perturbed */
+  double vpvs_min, vpvs_max;
+  int has_mantle;                      /* priors['mantle'] = (vs_m, vpvs_m) */
+  double mantle_vs, mantle_vpvs;
+  int noise_fixed[2 * BH_MAX_TARGETS]; /* per target (corr, sigma): prior given as a float */
+  double noise_min[2 * BH_MAX_TARGETS], noise_max[2 * BH_MAX_TARGETS];
+  /* initparams */
+  double thickmin;
+  int has_lvz, has_hvz;                /* initparams['lvz'] / ['hvz'] not None */
+  double lvz, hvz;
+  double propdist[5];                  /* vs, z, birth/death, noise, vpvs */
+  double acceptance[2];                /* percent */
+  int iter_burnin, iter_main;
+  int max_accepted;                    /* rows of the chain arrays per chain (reference:
+                                          iterations * max(acceptance) / 100); further accepted
+                                          models are counted in `overflow` and not stored */
+  unsigned long long seed;
+} bh_sampler_config;
+
+typedef struct bh_sampler bh_sampler;
+
+/* nchains chains with global indices first_chain .. first_chain + nchains - 1 on the
+ * engine's device.  ntargets must equal the engine's.  The engine must outlive the sampler
+ * and have max_batch >= nchains, max_layers >= layers_max + 1. */
+int bh_sampler_create(bh_engine* e, const bh_sampler_config* cfg, int ntargets, int nchains,
+                      long long first_chain, bh_sampler** out);
+void bh_sampler_destroy(bh_sampler* s);
+
+/* Initial state, HOST pointers: models [B][2*(layers_max+1)] with vs of the k[b] nuclei at
+ * [0, k) of the first half and their depths at [0, k) of the second half, ordered by depth;
+ * vpvs [B]; noise [B][2T].  Evaluates the models and makes them row 0 of the chain arrays
+ * (SingleChain._init_model_and_currentvalues, src/SingleChain.py:70-92). */
+int bh_sampler_init(bh_sampler* s, const double* models, const int* k, const double* vpvs,
+                    const double* noise);
+
+/* niter lock-step iterations of every chain; returns when they are done. */
+int bh_sampler_run(bh_sampler* s, int niter);
+
+/* Current state to HOST buffers (any pointer may be NULL): models/k/vpvs/noise as in
+ * bh_sampler_init, logL [B], misfits [B][T+1], propdist [B][5], accepted/proposed [B][5],
+ * iiter [B], nstored [B] rows used in the chain arrays, overflow [1]. */
+int bh_sampler_get_state(bh_sampler* s, double* models, int* k, double* vpvs, double* noise,
+                         double* logL, double* misfits, double* propdist, long long* accepted,
+                         long long* proposed, long long* iiter, int* nstored, long long* overflow);
+
+/* Chain arrays of chains [chain0, chain0 + nchain) to HOST buffers (float32, NaN padded, the
+ * layout of the reference's shared arrays): models [n][S][2*(layers_max+1)] (2k values, then
+ * NaN), misfits [n][S][T+1], likes [n][S], noise [n][S][2T], vpvs [n][S]; iters [n][S] int32 is
+ * SingleChain.chainiter (iteration at which the row was accepted). */
+int bh_sampler_get_chains(bh_sampler* s, int chain0, int nchain, float* models, float* misfits,
+                          float* likes, float* noise, float* vpvs, int* iters);
+
+/* Testing / resuming: overwrite the whole state (NULL = keep), read the last proposal, and
+ * replace the Philox variates of the following iterations by draws [B][4] =
+ * (u_mod, u_idx, gauss, u_acc) (NULL switches back to Philox). */
+int bh_sampler_set_state(bh_sampler* s, const double* models, const int* k, const double* vpvs,
+                         const double* noise, const double* logL, const double* misfits,
+                         const double* propdist, const long long* accepted,
+                         const long long* proposed, const long long* iiter);
+int bh_sampler_get_proposal(bh_sampler* s, double* models, int* k, double* vpvs, double* noise,
+                            int* valid, int* modify, double* dvs2, double* logL, double* misfits);
+int bh_sampler_set_forced_draws(bh_sampler* s, const double* draws);
+
 /* Diagnostics: evaluates the engine's straight-line fp64 elementary functions on
  * the device for n HOST values x; out[7][n] = exp(-|x|), sin x, cos x, 1/x,
  * sqrt|x|, 1/sqrt|x|, 1.0/x (faithful division).  Used by the accuracy tests. */

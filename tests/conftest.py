@@ -28,7 +28,7 @@ def _build_host_sim(name, defines=()):
     src = os.path.join(ROOT, "tests", "host_sim", "core_sim.cpp")
     so = os.path.join(ROOT, "tests", "host_sim", name)
     deps = [src] + [os.path.join(ROOT, "bayhunter_b200", "csrc", f)
-                    for f in ("bh_common.cuh", "bh_math.cuh", "swd_core.cuh", "swd_general_core.cuh", "rf_core.cuh")]
+                    for f in ("bh_common.cuh", "bh_math.cuh", "swd_core.cuh", "swd_general_core.cuh", "sampler_core.cuh", "rf_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] +
                        ["-D" + d for d in defines] + ["-o", so, src, "-lm"], check=True)

@@ -8,7 +8,9 @@
 #include <cstdlib>
 #include <vector>
 
+#include "../../include/bayhunter_b200.h"
 #include "../../bayhunter_b200/csrc/rf_core.cuh"
+#include "../../bayhunter_b200/csrc/sampler_core.cuh"
 #include "../../bayhunter_b200/csrc/swd_core.cuh"
 #include "../../bayhunter_b200/csrc/swd_general_core.cuh"
 
@@ -88,6 +90,44 @@ int swd_sim_general(const float* rows4, int nlayer, int wave, int igr, int kmax,
   int err = swd_general_curve(rows.data(), 1, nlayer, wave, igr, kmax, mode, flsph, periods, cg, &n);
   if (nsec) *nsec = (long long)n;
   return err;
+}
+
+// ---- sampler core (sampler_core.cuh): what one thread of the propose / accept kernels runs ----
+void sampler_sim_philox(uint32_t* ctr, const uint32_t* key) { philox4x32_10(ctr, key[0], key[1]); }
+
+void sampler_sim_draw(unsigned long long seed, unsigned long long chain, long long iter, double* out4) {
+  Draw d = sampler_draw(seed, chain, iter);
+  out4[0] = d.u_mod; out4[1] = d.u_idx; out4[2] = d.gauss; out4[3] = d.u_acc;
+}
+
+// model: [2*maxl], vs of the k nuclei in the first half, depths in the second; in/out.
+// rows: [maxl*4] packed engine rows of the proposal (valid proposals only).  Returns valid.
+int sampler_sim_propose(const bh_sampler_config* cfg, int ntargets, long long iiter, const double* propdist,
+                        const double* draws4, double* model, int* k, double* vpvs, double* noise,
+                        int* modify, double* dvs2, double* rows) {
+  SamplerCfg c = sampler_cfg_from_public(*cfg, ntargets);
+  const int maxl = c.maxlayers;
+  double vs[SMP_MAX_ROWS], z[SMP_MAX_ROWS], h[SMP_MAX_ROWS];
+  for (int i = 0; i < *k; ++i) { vs[i] = model[i]; z[i] = model[maxl + i]; }
+  Draw d; d.u_mod = draws4[0]; d.u_idx = draws4[1]; d.gauss = draws4[2]; d.u_acc = draws4[3];
+  int valid = sampler_propose(c, iiter, propdist, d, vs, z, k, vpvs, noise, modify, dvs2, h);
+  if (*k > maxl) valid = 0;
+  const int kk = *k < maxl ? *k : maxl;
+  for (int i = 0; i < kk; ++i) { model[i] = vs[i]; model[maxl + i] = z[i]; }
+  if (valid) sampler_pack_rows(c, vs, h, *k, *vpvs, rows);
+  return valid;
+}
+
+double sampler_sim_alpha(const bh_sampler_config* cfg, int ntargets, int modify, const double* propdist,
+                         double dvs2, double like_prop, double like_cur) {
+  SamplerCfg c = sampler_cfg_from_public(*cfg, ntargets);
+  return sampler_alpha(c, modify, propdist, dvs2, like_prop, like_cur);
+}
+
+void sampler_sim_adjust(const bh_sampler_config* cfg, int ntargets, double* propdist, const long long* accepted,
+                        const long long* proposed) {
+  SamplerCfg c = sampler_cfg_from_public(*cfg, ntargets);
+  sampler_adjust_propdist(c, propdist, accepted, proposed);
 }
 
 // Receiver function through rf_core.cuh; same arguments as synrf_cwrap minus fz/fr.
