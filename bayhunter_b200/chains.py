@@ -101,3 +101,58 @@ def outlier_chains(likes, dev=0.05):
     bad = (1 - scores) > dev
     idx = torch.nonzero(bad).flatten()
     return idx, (1 - scores)[idx]
+
+
+def save_final_distribution(datapath, maxmodels=200000, dev=0.05, rstate=None):
+    """Pool the main-phase chain files into the final posterior files, like
+    PlotFromStorage.save_final_distribution (src/Plotting.py:161-258): chains whose median
+    likelihood deviates more than `dev` from the best chain are dropped (get_outliers :113-154,
+    `outliers.dat` written), the others contribute maxmodels / nchains models each (random
+    subset, order kept), and c_models / c_likes / c_misfits / c_noise / c_vpvs .npy are saved.
+    Reads the per-chain files MCMC_Optimizer wrote; returns the pooled arrays."""
+    import glob
+    import os
+    import os.path as op
+    if rstate is None:
+        rstate = np.random.RandomState(333)          # module-level rstate of the reference's Plotting.py
+    names = ['models', 'likes', 'misfits', 'noise', 'vpvs']
+    files = {n: sorted(glob.glob(op.join(datapath, 'c???_p2%s.npy' % n))) for n in names}
+    nfiles = {len(v) for v in files.values()}
+    if len(nfiles) != 1 or 0 in nfiles:
+        raise IOError('missing chain files in %s' % datapath)
+    cidx = np.array([int(op.basename(f)[1:4]) for f in files['likes']])
+    medians = np.array([np.median(np.load(f)) for f in files['likes']])
+    maxlike = np.max(medians)
+    scores = medians / maxlike if maxlike > 0 else maxlike / medians
+    bad = (1 - scores) > dev
+    outliers = cidx[bad]
+    outlierfile = op.join(datapath, 'outliers.dat')
+    if op.exists(outlierfile):
+        os.remove(outlierfile)
+    if outliers.size:
+        with open(outlierfile, 'w') as f:
+            f.write('# Outlier chainindices with %.3f deviation condition\n' % dev)
+            for c, sc in zip(outliers, (1 - scores)[bad]):
+                f.write('%d\t%.3f\n' % (c, sc))
+    nchains = int(cidx.size - outliers.size)
+    mpc = int(int(maxmodels) / nchains)
+    pooled = {n: [] for n in names}
+    for i, c in enumerate(cidx):
+        if c in outliers:
+            continue
+        n = len(np.load(files['likes'][i]))
+        index = np.arange(n).astype(int)
+        if n > mpc:
+            index = rstate.choice(index, mpc, replace=False)
+            index.sort()
+        for name in names:
+            pooled[name].append(np.load(files[name][i])[index])
+    out = {}
+    for name in names:
+        out[name] = np.concatenate(pooled[name], axis=0)
+    keep = ~np.isnan(out['likes'])
+    for name in names:
+        out[name] = out[name][keep]
+        np.save(op.join(datapath, 'c_%s' % name), out[name])
+    out['outliers'] = outliers
+    return out

@@ -409,3 +409,20 @@ def test_device_elementary_functions_accuracy():
     assert ulps(out[4][norm], np.sqrt(np.abs(x[norm]))).max() <= 1.0
     assert ulps(out[5][norm], 1.0 / np.sqrt(np.abs(x[norm]))).max() <= 2.0
     assert ulps(out[6][norm], 1.0 / x[norm]).max() <= 1.0
+
+
+def test_synthobs_reproduces_tutorial_observed_files(golden_dir, tmp_path):
+    """SynthObs.return_swddata / return_rfdata / save_data: the reference generated
+    tutorial/observed/st3_*.dat exactly this way (tutorial/create_testdata.py)."""
+    from bayhunter_b200 import SynthObs
+    swd = SynthObs.return_swddata(ST3_H, ST3_VS, vpvs=1.73, x=np.loadtxt(golden_dir + "/st3_rdispph.dat")[:, 0])
+    rf = SynthObs.return_rfdata(ST3_H, ST3_VS, vpvs=1.73, x=np.loadtxt(golden_dir + "/st3_prf.dat")[:, 0])
+    data = dict(swd); data.update(rf)
+    SynthObs.save_data(data, outfile=str(tmp_path / "st3_%s.dat"))
+    SynthObs.save_model(ST3_H, ST3_VS, vpvs=1.73, outfile=str(tmp_path / "st3_mod.dat"))
+    for ref in ("rdispph", "rdispgr", "ldispph", "ldispgr", "prf", "srf"):
+        got = np.loadtxt(tmp_path / ("st3_%s.dat" % ref))
+        want = np.loadtxt(golden_dir + "/st3_%s.dat" % ref)
+        assert np.allclose(got[:, 0], want[:, 0], atol=1e-4)
+        assert np.abs(got[:, 1] - want[:, 1]).max() <= 1.01e-4, ref      # both sides printed with 4 decimals
+    assert open(tmp_path / "st3_mod.dat").read().split() == open(golden_dir + "/st3_mod.dat").read().split()

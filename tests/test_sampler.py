@@ -209,3 +209,35 @@ def test_chain_files_match_reference_weighting(tmp_path):
         for name in ("models", "likes", "misfits", "noise", "vpvs"):
             got = np.load(tmp_path / ("c007_p%d%s.npy" % (phase, name)))
             assert np.array_equal(got, arr[name][idx])
+
+
+def test_save_final_distribution_matches_reference(tmp_path, golden_dir):
+    """chains.save_final_distribution on the same per-chain files == what the reference's
+    PlotFromStorage.save_final_distribution wrote (outlier chain, per-chain random subset, pooled
+    arrays), fixture made by tests/golden/make_pooling_fixtures.py."""
+    from bayhunter_b200 import chains
+    fx = np.load(os.path.join(golden_dir, "ref_final_distribution.npz"))
+    for c in range(6):
+        for name in ("models", "likes", "misfits", "noise", "vpvs"):
+            for phase in (1, 2):
+                np.save(tmp_path / ("c%.3d_p%d%s" % (c, phase, name)), fx["in_c%d_%s" % (c, name)])
+    out = chains.save_final_distribution(str(tmp_path), maxmodels=int(fx["maxmodels"][0]), dev=float(fx["dev"][0]),
+                                         rstate=np.random.RandomState(333))
+    assert list(out["outliers"]) == list(fx["outliers"])
+    assert np.loadtxt(tmp_path / "outliers.dat", usecols=[0], dtype=int).tolist() == int(fx["outliers"][0])
+    for name in ("models", "likes", "misfits", "noise", "vpvs"):
+        got = np.load(tmp_path / ("c_%s.npy" % name))
+        assert np.array_equal(got, fx["out_" + name], equal_nan=True), name
+
+
+def test_synthobs_noise_matches_reference(golden_dir):
+    """SynthObs.compute_expnoise / compute_gaussnoise reproduce the reference's draws from its
+    module RandomState(333)."""
+    from bayhunter_b200 import SynthObs as so_mod
+    import bayhunter_b200.SynthObs as mod
+    fx = np.load(os.path.join(golden_dir, "ref_synthobs_noise.npz"))
+    mod.rstate = np.random.RandomState(333)
+    for n in (20, 201):
+        y = np.zeros(n)
+        assert np.array_equal(so_mod.compute_expnoise(y, corr=0.6, sigma=0.02), fx["exp_%d" % n])
+        assert np.array_equal(so_mod.compute_gaussnoise(y, corr=0.9, sigma=0.005), fx["gauss_%d" % n])
