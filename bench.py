@@ -142,7 +142,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--cpu-per-core", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool-samples", type=int, default=100)
+    ap.add_argument("--sampler-iters", type=int, default=40,
+                    help="lock-step MCMC iterations timed for the auxiliary 'sampler' object (0: skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -350,8 +352,42 @@ def main():
         pool_ms = e0.elapsed_time(e1)
         assert pooled["likes"].shape[0] == world * B
 
+    # ---- auxiliary: the device sampler around the same hot path ----
+    # B chains advance in lock step (propose kernel -> engine -> accept kernel, no host round trip);
+    # reported beside the headline metric, not part of it.
+    smp = None
+    if args.sampler_iters > 0:
+        from bayhunter_b200 import Targets as T_, SingleChain as sc
+        cls = {"rdispph": T_.RayleighDispersionPhase, "rdispgr": T_.RayleighDispersionGroup,
+               "ldispph": T_.LoveDispersionPhase, "ldispgr": T_.LoveDispersionGroup,
+               "prf": T_.PReceiverFunction, "srf": T_.SReceiverFunction}
+        jt = T_.JointTarget([cls[ref](x, y) for ref, x, y in targets])
+        nr = c["nrows"]
+        lay = (nr - 1, nr - 1 + 3) if np.isscalar(nr) else (nr[0] - 1, nr[1] - 1)
+        priors = dict(vs=(2, 5), z=(0, 60), layers=lay, vpvs=(1.4, 2.1), swdnoise_corr=0.,
+                      swdnoise_sigma=(1e-5, 0.1), rfnoise_corr=(0.35, 0.75), rfnoise_sigma=(1e-5, 0.05))
+        ip = dict(iter_burnin=100000, iter_main=50000, thickmin=0.1, acceptance=(40, 45))
+        lo = rank * B
+        ens = sc.ChainEnsemble(jt, priors, ip, nchains=B, first_chain=lo, seed=20260101, max_accepted=64,
+                               chain_seeds=np.arange(lo, lo + B) + 7)
+        ens.init()
+        ens.run(3)
+        barrier()
+        t0 = time.perf_counter()
+        ens.run(args.sampler_iters)
+        torch.cuda.synchronize(dev)
+        smp_s = time.perf_counter() - t0
+        st = ens.state()
+        smp = dict(seconds=smp_s, proposed=float(st["proposed"].sum()), accepted=float(st["accepted"].sum()),
+                   iters=args.sampler_iters + 3, mean_rows=float(st["k"].mean()), layers_prior=list(lay))
+        ens.close()
+
     # ---- max over ranks ----
     if world > 1:
+        if smp is not None:
+            tt = torch.tensor([smp["seconds"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            smp["seconds"] = float(tt[0])
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
@@ -416,6 +452,16 @@ def main():
         }
         if pool_ms is not None:
             line["pool_allgather_ms"] = pool_ms
+        if smp is not None:
+            line["sampler"] = {
+                "chain_iterations_per_s": world * B * args.sampler_iters / smp["seconds"],
+                "ms_per_lockstep_iteration": 1e3 * smp["seconds"] / args.sampler_iters,
+                "evaluated_fraction": smp["proposed"] / (B * smp["iters"]),
+                "accept_rate": smp["accepted"] / max(1.0, smp["proposed"]),
+                "mean_rows": smp["mean_rows"], "layers_prior": smp["layers_prior"],
+                "what": "bh_sampler_run: B chains per GPU in lock step on the device (proposal, prior check, "
+                        "forward models, likelihood, Metropolis-Hastings, proposal-width control); rank-0 "
+                        "statistics, wall clock max over ranks"}
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(targets, batches[-1], nlay, noise, args.cpu_per_core)
             cb.pop("seconds", None)
