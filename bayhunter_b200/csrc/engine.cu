@@ -80,6 +80,9 @@ struct bh_engine {
   int* tstatus = nullptr;
   unsigned long long* counters = nullptr;
   int* swd_queue = nullptr;   // work-item counters of the mixed dispersion launch
+  int* swd_perm = nullptr;    // [max_batch] models ordered by layer count (ragged batches)
+  int sort_layers = 1;        // deal models to dispersion warps in that order
+  int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
   int nsm = 0;
   int max_nfreq = 0;
   // device mirrors for the host-pointer entry point
@@ -92,6 +95,7 @@ struct bh_engine {
   int searches_per_warp = 0;  // phase-velocity curves; 0 = auto
   int group_spw = 0;          // group-velocity curves; 0 = half of the above
   int max_spec = 8;
+  int spw_curve[4] = {0, 0, 0, 0};   // per curve type override: Rayleigh group, Rayleigh phase, Love group, Love phase
   int split_waves = 0;        // 1: Rayleigh and Love curves in separate launches (two streams)
   int rayleigh_sm_pct = 0;    // mixed launch: share of the SMs dedicated to the Rayleigh items (0 = no partition)
   int direct = 0;             // 0 never, 1 when warps are full of chains, 2 always
@@ -259,6 +263,7 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
   if (rc == BH_OK) rc = scratch(e, &e->tstatus, B * kMaxTargets);
   if (rc == BH_OK) rc = scratch(e, &e->counters, BH_NUM_COUNTERS);
   if (rc == BH_OK) rc = scratch(e, &e->swd_queue, 2 + 1024);
+  if (rc == BH_OK) rc = scratch(e, &e->swd_perm, B);
   if (rc == BH_OK) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -300,12 +305,22 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "swd_group_searches_per_warp")) {
     if (value < 0 || value > 32 || (value & (value - 1))) return set_err(BH_ERR_ARG, "group searches_per_warp must be 0 (auto) or a power of two <= 32");
     e->group_spw = value;
+  } else if (!strncmp(key, "swd_spw_", 8) && strlen(key) == 10) {
+    // swd_spw_rg / swd_spw_rp / swd_spw_lg / swd_spw_lp: models per warp of one curve type (0 = rule above)
+    const int w = key[8] == 'r' ? 0 : key[8] == 'l' ? 2 : -1, g = key[9] == 'g' ? 0 : key[9] == 'p' ? 1 : -1;
+    if (w < 0 || g < 0) return set_err(BH_ERR_ARG, "unknown tunable");
+    if (value < 0 || value > (g == 0 ? 16 : 32) || (value & (value - 1))) return set_err(BH_ERR_ARG, "models per warp must be 0 or a power of two (<= 16 for group curves)");
+    e->spw_curve[w + g] = value;
   } else if (!strcmp(key, "swd_max_spec")) {
     if (value < 1 || value > 32) return set_err(BH_ERR_ARG, "swd_max_spec must be 1..32");
     e->max_spec = value;
   } else if (!strcmp(key, "swd_rayleigh_sm_pct")) {
     if (value < 0 || value > 100) return set_err(BH_ERR_ARG, "swd_rayleigh_sm_pct must be 0..100");
     e->rayleigh_sm_pct = value;
+  } else if (!strcmp(key, "rf_after_love")) {
+    e->rf_after_love = value ? 1 : 0;
+  } else if (!strcmp(key, "swd_sort_layers")) {
+    e->sort_layers = value ? 1 : 0;
   } else if (!strcmp(key, "swd_split_waves")) {
     e->split_waves = value ? 1 : 0;
   } else if (!strcmp(key, "swd_direct")) {
@@ -394,7 +409,8 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   bool love_forked = false;
   if (nswd > 0 || gen.ncurves > 0) {
     { KTimer kt(e, BH_K_PREP_SWD, st);
-      launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st); }
+      launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st);
+      if (e->sort_layers && nswd > 0) launch_layer_order(nlay, B, e->swd_perm, nullptr, st); }
     // models per warp: phase curves S (one chain per model), group curves S_g <= 16
     // (two chains per model).  Fewer models per warp = more spare lanes for bracket
     // speculation = fewer rounds, but more warps to issue.  Measured on B200
@@ -432,10 +448,18 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       SwdLaunch& sw = swl[w];
       if (sw.ncurves == 0) continue;
       sw.rows = prep.swd_rows; sw.row_stride = prep.swd_stride; sw.nlay = nlay; sw.B = B;
+      sw.perm = e->sort_layers ? e->swd_perm : nullptr;
       sw.curves = e->curves; sw.roots = e->roots; sw.curve_stride = e->curve_stride;
       sw.tstatus = e->tstatus; sw.counters = e->counters;
       sw.lcap = lmax;
-      for (int c = 0; c < sw.ncurves; ++c) sw.spw[c] = sw.igr[c] ? Sg : S;
+      for (int c = 0; c < sw.ncurves; ++c) {
+        sw.spw[c] = sw.igr[c] ? Sg : S;
+        const int ov = e->spw_curve[(sw.wave[c] == 2 ? 0 : 2) + (sw.igr[c] ? 0 : 1)];
+        if (ov > 0) {
+          sw.spw[c] = ov;
+          while (sw.spw[c] > 1 && swd_smem_bytes(lmax, sw.spw[c]) > 24 * 1024) sw.spw[c] >>= 1;
+        }
+      }
       sw.max_spec = e->max_spec;
       sw.direct = (e->direct == 2 || (e->direct == 1 && S == 32 && Sg == 16)) ? 1 : 0;
       cudaStream_t sst = st;
@@ -457,6 +481,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
     }
   }
+  if (love_forked && e->rf_after_love && st_rf != st) st_rf = e->s_aux2;
   for (int t = 0; t < ts.ntargets; ++t) {
     const TargetDev& d = ts.t[t];
     if (!is_rf(d.ref)) continue;
@@ -477,7 +502,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     { KTimer kt(e, BH_K_RF_SPECTRUM, st_rf); launch_rf_spectrum(rf, st_rf); }
     { KTimer kt(e, BH_K_RF_SYNTH, st_rf); launch_rf_synth(rf, st_rf); }
   }
-  if (st_rf != st) {
+  if (st_rf != st && st_rf != e->s_aux2) {
     BH_CUDA(cudaEventRecord(e->ev_join, st_rf));
     BH_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
   }

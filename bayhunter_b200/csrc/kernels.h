@@ -68,6 +68,9 @@ struct PrepOut {
 void launch_prepare(const double* model, const int* nlay, const double* rho, int B, int lmax,
                     bool want_swd, bool want_rf, double rf_p, double rf_nsv, double rf_qp,
                     double rf_qs, PrepOut out, cudaStream_t st);
+// perm[B]: model indices ordered by decreasing layer count (counting sort; order within a layer
+// count is arbitrary).  scratch: int[2 * 128], zeroed by the call.
+void launch_layer_order(const int* nlay, int B, int* perm, int* scratch, cudaStream_t st);
 // explicit single-model arrays for the synrf shim (z, vp, vs, rho, qp, qs as given)
 void launch_prepare_rf_explicit(const double* z, const double* vp, const double* vs,
                                 const double* rho, const double* qp, const double* qs, int nlay,
@@ -79,6 +82,7 @@ struct SwdLaunch {
   int row_stride;
   int lcap;                     // layer capacity of the shared-memory records (>= max nlay)
   const int* nlay;
+  const int* perm;              // [B] order in which models are dealt to warps (null: 0, 1, 2, ...)
   int B;
   int ncurves;
   int target_id[kMaxTargets];   // index into TargetSet for each curve

@@ -118,6 +118,35 @@ __global__ void prepare_rf_explicit_kernel(const double* __restrict__ z, const d
            out.rf_coef + (size_t)li * 4, out.rf_mc);
 }
 
+// Counting sort of the models by layer count, longest first: one CTA; the bins live in shared memory.
+__global__ void __launch_bounds__(1024)
+layer_order_kernel(const int* __restrict__ nlay, int B, int* __restrict__ perm) {
+  __shared__ int hist[128], start[128];
+  const int t = threadIdx.x;
+  if (t < 128) hist[t] = 0;
+  __syncthreads();
+  for (int b = t; b < B; b += blockDim.x) {
+    int n = nlay[b]; n = n < 0 ? 0 : (n > 127 ? 127 : n);
+    atomicAdd(&hist[n], 1);
+  }
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int n = 127; n >= 0; --n) { start[n] = acc; acc += hist[n]; }
+  }
+  __syncthreads();
+  for (int b = t; b < B; b += blockDim.x) {
+    int n = nlay[b]; n = n < 0 ? 0 : (n > 127 ? 127 : n);
+    perm[atomicAdd(&start[n], 1)] = b;
+  }
+}
+
+void launch_layer_order(const int* nlay, int B, int* perm, int* scratch, cudaStream_t st) {
+  (void)scratch;
+  if (B <= 0) return;
+  layer_order_kernel<<<1, 1024, 0, st>>>(nlay, B, perm);
+}
+
 void launch_prepare(const double* model, const int* nlay, const double* rho, int B, int lmax,
                     bool want_swd, bool want_rf, double rf_p, double rf_nsv, double rf_qp,
                     double rf_qs, PrepOut out, cudaStream_t st) {

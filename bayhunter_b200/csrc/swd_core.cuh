@@ -251,6 +251,13 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
 #ifndef BH_SWD_WIDE
 #define BH_SWD_WIDE 0
 #endif
+// Love layers whose (vector-independent) terms are formed side by side: 1, 2 or 4
+#ifndef BH_P_SINCOS_COND
+#define BH_P_SINCOS_COND 1
+#endif
+#ifndef BH_LOVE_GROUP
+#define BH_LOVE_GROUP (BH_SWD_WIDE ? 4 : 1)
+#endif
 constexpr int SWD_REC_FIELDS = 6;
 // Rayleigh record fields
 enum { RR_D = 0, RR_IA = 1, RR_IB = 2, RR_RHO = 3, RR_IRHO = 4, RR_TB2 = 5 };
@@ -311,28 +318,47 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   BH_N(r[i] = fma(-g[i], g[i], s[i]))
   BH_N(g[i] = fma(r[i], hh[i], g[i]); hh[i] = hh[i] + hh[i])      // g = sqrt(s), hh = 1/sqrt(s)
   BH_N(p[i] = g[i] * d[i]; pm[i] = osc[i] ? 0.0 : p[i])
-  // exp(-pm) and sincos(p), step by step side by side
+  // exp(-pm) and sincos(p), step by step side by side.  With BH_P_SINCOS_COND the P half of a
+  // Rayleigh layer (i = 0 of N = 2) takes its sincos only when some lane of the warp has an
+  // oscillatory P term (c > vp of that layer: rare) -- a warp-uniform branch.
+#if BH_P_SINCOS_COND
+  constexpr int I0 = (N == 2) ? 1 : 0;
+#else
+  constexpr int I0 = 0;
+#endif
   double te[N], ts[N], fe[N], ft[N], re[N], rt[N], z[N], pe[N], ps[N], pc[N];
   int ne[N], q[N];
-  BH_N(te[i] = fma(-pm[i], BH_K(K_LOG2E), BH_K(K_MAGIC)); ts[i] = fma(p[i], BH_K(K_TWO_OVER_PI), BH_K(K_MAGIC)))
-  BH_N(ne[i] = __double2loint(te[i]); q[i] = __double2loint(ts[i]);
-       fe[i] = te[i] - BH_K(K_MAGIC); ft[i] = ts[i] - BH_K(K_MAGIC))
-  BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_HI), -pm[i]); rt[i] = fma(-ft[i], BH_K(K_PIO2_1), p[i]))
-  BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_LO), re[i]); rt[i] = fma(-ft[i], BH_K(K_PIO2_2), rt[i]))
-  BH_N(pe[i] = fma(BH_K_E13, re[i], BH_K_E12); rt[i] = fma(-ft[i], BH_K(K_PIO2_3), rt[i]))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E11); z[i] = rt[i] * rt[i])
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E10); ps[i] = fma(BH_K_S6, z[i], BH_K(K_S5)); pc[i] = fma(BH_K_C6, z[i], BH_K(K_C5)))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E9)); ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4)))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E8)); ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3)))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E7)); ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2)))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E6)); ps[i] = fma(ps[i], z[i], BH_K(K_S1)); pc[i] = fma(pc[i], z[i], BH_K(K_C1)))
   double sn[N], cn[N], hz[N], w1[N];
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E5)); sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); hz[i] = 0.5 * z[i])
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E4)); w1[i] = 1.0 - hz[i]; pc[i] = z[i] * z[i] * pc[i])
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E3)); cn[i] = w1[i] + (((1.0 - w1[i]) - hz[i]) + pc[i]))
+#define BH_SC(...) if (i >= I0) { __VA_ARGS__; }
+  BH_N(te[i] = fma(-pm[i], BH_K(K_LOG2E), BH_K(K_MAGIC)); BH_SC(ts[i] = fma(p[i], BH_K(K_TWO_OVER_PI), BH_K(K_MAGIC))))
+  BH_N(ne[i] = __double2loint(te[i]); fe[i] = te[i] - BH_K(K_MAGIC);
+       BH_SC(q[i] = __double2loint(ts[i]); ft[i] = ts[i] - BH_K(K_MAGIC)))
+  BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_HI), -pm[i]); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_1), p[i])))
+  BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_LO), re[i]); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_2), rt[i])))
+  BH_N(pe[i] = fma(BH_K_E13, re[i], BH_K_E12); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_3), rt[i])))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E11); BH_SC(z[i] = rt[i] * rt[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E10); BH_SC(ps[i] = fma(BH_K_S6, z[i], BH_K(K_S5)); pc[i] = fma(BH_K_C6, z[i], BH_K(K_C5))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E9)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E8)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E7)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E6)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S1)); pc[i] = fma(pc[i], z[i], BH_K(K_C1))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E5)); BH_SC(sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); hz[i] = 0.5 * z[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E4)); BH_SC(w1[i] = 1.0 - hz[i]; pc[i] = z[i] * z[i] * pc[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E3)); BH_SC(cn[i] = w1[i] + (((1.0 - w1[i]) - hz[i]) + pc[i])))
   BH_N(pe[i] = fma(pe[i], re[i], 0.5))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
+#undef BH_SC
+#if BH_P_SINCOS_COND
+  if (I0 == 1) {
+    q[0] = 0; sn[0] = 0.0; cn[0] = 1.0;
+    if (__any_sync(__activemask(), osc[0])) {
+      double a, c;
+      fm::sincos_cw(p[0], &a, &c);        // the same sequence as above (bh_math.cuh), quadrant already applied
+      sn[0] = a; cn[0] = c;
+    }
+  }
+#endif
   double em[N], fac[N], ch[N], sh[N];
   BH_N(em[i] = fm::hi_lo(__double2hiint(pe[i]) + (int)((unsigned)ne[i] << 20), __double2loint(pe[i])))
   // quadrant fix-up of sin/cos: swap on bit 0, sign flips as XORs on the high words
@@ -426,17 +452,18 @@ BH_HD double secular_love_rec(const double* rec, int fs, int ls, int L, double w
   if (L < 2) return e1;
   int l = L - 2;
 #pragma unroll 1
-  for (int r = BH_SWD_WIDE ? ((L - 1) & 3) : (L - 1); r > 0; --r, --l) {
+  for (int r = (BH_LOVE_GROUP > 1) ? ((L - 1) % BH_LOVE_GROUP) : (L - 1); r > 0; --r, --l) {
     LoveLayer m;
     love_layers_n<1>(rec, fs, ls, l, wvno, omega, &m);
     love_apply(m, e1, e2);
   }
-#if BH_SWD_WIDE
+#if BH_LOVE_GROUP > 1
 #pragma unroll 1
-  for (int g = (L - 1) >> 2; g > 0; --g, l -= 4) {     // layers l .. l-3
-    LoveLayer m[4];
-    love_layers_n<4>(rec, fs, ls, l, wvno, omega, m);
-    love_apply(m[0], e1, e2); love_apply(m[1], e1, e2); love_apply(m[2], e1, e2); love_apply(m[3], e1, e2);
+  for (int g = (L - 1) / BH_LOVE_GROUP; g > 0; --g, l -= BH_LOVE_GROUP) {     // layers l .. l-G+1
+    LoveLayer m[BH_LOVE_GROUP];
+    love_layers_n<BH_LOVE_GROUP>(rec, fs, ls, l, wvno, omega, m);
+#pragma unroll
+    for (int j = 0; j < BH_LOVE_GROUP; ++j) love_apply(m[j], e1, e2);
   }
 #endif
   double xnor = fm::absmax(e1, e2);

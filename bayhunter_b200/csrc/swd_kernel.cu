@@ -23,8 +23,11 @@
 #include "kernels.h"
 
 // resident warps (= CTAs) per SM the register allocation must allow
+// 14: the compiler fits the Rayleigh instantiations into 128 registers without spilling, so the
+// whole grid of a batch (~2048 warps) is resident at once instead of leaving a second wave
+// (measured: dispersion kernel 4.65 -> 4.2 ms alone, profiles/r01_variants.txt)
 #ifndef BH_SWD_MIN_BLOCKS_RAYLEIGH
-#define BH_SWD_MIN_BLOCKS_RAYLEIGH 12
+#define BH_SWD_MIN_BLOCKS_RAYLEIGH 14
 #endif
 #ifndef BH_SWD_MIN_BLOCKS_LOVE
 #define BH_SWD_MIN_BLOCKS_LOVE 16
@@ -101,6 +104,11 @@ swd_kernel(SwdLaunch p) {
   const int stride = p.row_stride;                    // rows per model in p.rows
   const int lcap = p.lcap;                            // layer capacity of the records
 
+  // model handled by slot j of this warp: models are dealt to warps in the order of p.perm
+  // (sorted by layer count, so that the lanes of a warp run layer loops of similar length)
+  const int* __restrict__ perm = p.perm;
+#define BH_MODEL(j) (perm ? perm[b0 + (j)] : b0 + (j))
+
   // ---- shared-memory carve-up: [records 6*lcap*S doubles][WarpShared] ----
   double* rec = reinterpret_cast<double*>(smem_raw);
   const int fs = lcap * S;                            // field stride; layer stride = S
@@ -120,15 +128,16 @@ swd_kernel(SwdLaunch p) {
   ctx.omA = ws->omA; ctx.omB = ws->omB;
   ctx.link = (igr > 0 && owner) ? &ws->link[sidx] : nullptr;
   {
-    double* r = p.roots + ((size_t)(b0 + (owner ? sidx : 0)) * p.curve_stride + p.curve_off[curve]) * 2;
+    double* r = p.roots + ((size_t)BH_MODEL(owner ? sidx : 0) * p.curve_stride + p.curve_off[curve]) * 2;
     ctx.ra = r; ctx.rb = r + kmax;
   }
   int myL = 0;
+  const int mymodel = owner ? BH_MODEL(sidx) : 0;
   __syncwarp();
   if (owner) {
-    myL = p.nlay[b0 + sidx];
+    myL = p.nlay[mymodel];
     if (myL > lcap) myL = lcap;
-    if (search_setup(s, p.rows + (size_t)(b0 + sidx) * stride, 1, myL, kmax, role, ws->tab + lane, 32)) {
+    if (search_setup(s, p.rows + (size_t)mymodel * stride, 1, myL, kmax, role, ws->tab + lane, 32)) {
       if (role == 0) search_begin_a(s, ctx);
     } else if (role == 0 && ctx.link) {
       ctx.link->a_failed = 1;
@@ -146,7 +155,7 @@ swd_kernel(SwdLaunch p) {
     if (m < nsearch) {
       const int L = ws->nlay[m];
       if (l < L) {
-        const LayerRow r = p.rows[(size_t)(b0 + m) * stride + l];
+        const LayerRow r = p.rows[(size_t)BH_MODEL(m) * stride + l];
         swd_make_rec(wave, r, l == L - 1, rec + (size_t)l * S + m, fs);
       }
     }
@@ -245,14 +254,15 @@ swd_kernel(SwdLaunch p) {
     if (owner && role == 0) {
       bool ok = done;
       if (igr > 0) ok = ok && ((bdone >> (lane + S)) & 1u);
-      double* __restrict__ my_curve = p.curves + (size_t)(b0 + sidx) * p.curve_stride + p.curve_off[curve];
+      double* __restrict__ my_curve = p.curves + (size_t)mymodel * p.curve_stride + p.curve_off[curve];
       if (ok)
         for (int k = 0; k < kmax; ++k)
           my_curve[k] = swd_curve_value(igr, periods[k], ctx.ra[k], igr > 0 ? ctx.rb[k] : 0.0);
-      p.tstatus[(size_t)(b0 + sidx) * kMaxTargets + tid] = ok ? 1 : 0;
+      p.tstatus[(size_t)mymodel * kMaxTargets + tid] = ok ? 1 : 0;
     }
   }
 
+#undef BH_MODEL
   // ---- counters (one atomic per warp) ----
   for (int d = 16; d > 0; d >>= 1) {
     evaluated += __shfl_down_sync(0xffffffffu, evaluated, d);

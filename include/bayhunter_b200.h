@@ -109,6 +109,11 @@ int bh_engine_synth_stride(const bh_engine* e);
 /* Tunables (call before eval; all have working defaults).
  *   key "swd_searches_per_warp"  1..32   phase-velocity curves (default chosen from the batch size)
  *   key "swd_group_searches_per_warp" 1..32  group-velocity curves (default: half of the above)
+ *   key "swd_spw_rg" / "_rp" / "_lg" / "_lp"  models per warp of one curve type (Rayleigh/Love,
+ *                                        group/phase); 0 = the two keys above (default)
+ *   key "swd_sort_layers"        0/1     deal models to the dispersion warps sorted by layer count, so
+ *                                        that a warp's lanes run layer loops of similar length (default 1;
+ *                                        results do not depend on it)
  *   key "swd_direct"             0/1/2   chains evaluate only their own candidate: never (default) /
  *                                        when warps are full of chains / always
  *   key "swd_rayleigh_sm_pct"    0..100  one launch: share of the SMs whose CTAs take the Rayleigh work
