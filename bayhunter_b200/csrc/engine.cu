@@ -83,6 +83,7 @@ struct bh_engine {
   int* swd_perm = nullptr;    // [max_batch] models ordered by layer count (ragged batches)
   int sort_layers = 1;        // deal models to dispersion warps in that order
   int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
+  int rf_first = 0;           // enqueue the RF kernels before the dispersion kernels
   int nsm = 0;
   int max_nfreq = 0;
   // device mirrors for the host-pointer entry point
@@ -317,6 +318,8 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "swd_rayleigh_sm_pct")) {
     if (value < 0 || value > 100) return set_err(BH_ERR_ARG, "swd_rayleigh_sm_pct must be 0..100");
     e->rayleigh_sm_pct = value;
+  } else if (!strcmp(key, "rf_first")) {
+    e->rf_first = value ? 1 : 0;
   } else if (!strcmp(key, "rf_after_love")) {
     e->rf_after_love = value ? 1 : 0;
   } else if (!strcmp(key, "swd_sort_layers")) {
@@ -406,6 +409,30 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   }
 
   for (bool& u : e->pev_used) u = false;
+  // receiver-function launches of this evaluation (enqueued before or after the dispersion launches)
+  auto launch_rf = [&](cudaStream_t st_rf) {
+  for (int t = 0; t < ts.ntargets; ++t) {
+    const TargetDev& d = ts.t[t];
+    if (!is_rf(d.ref)) continue;
+    { KTimer kt(e, BH_K_PREP_RF, st_rf);
+      launch_prepare(model, nlay, rho, B, lmax, false, true, d.p, d.nsv, d.qp, d.qs, prep, st_rf); }
+    RfLaunch rf{};
+    rf.lay = prep.rf_lay; rf.coef = prep.rf_coef; rf.mc = prep.rf_mc; rf.nlay = nlay;
+    rf.B = B; rf.lmax = lmax;
+    rf.k.dw = 2.0 * RF_PI * d.fsamp / d.nsamp;
+    rf.k.wref = 2.0 * RF_PI * 1.0;
+    rf.k.a = d.gauss; rf.k.tshift = d.tshift;
+    rf.k.qn = sqrt(RF_PI) * d.fsamp / d.gauss;
+    rf.k.u = d.p * RF_DEG_PER_KM;
+    rf.k.waveno = d.waveno; rf.k.nsamp = d.nsamp;
+    rf.spec = e->spec;
+    rf.out = e->rfsynth; rf.out_stride = ts.synth_stride; rf.out_off = d.synth_off; rf.ndata = d.n;
+    rf.tstatus = e->tstatus; rf.target_id = t;
+    { KTimer kt(e, BH_K_RF_SPECTRUM, st_rf); launch_rf_spectrum(rf, st_rf); }
+    { KTimer kt(e, BH_K_RF_SYNTH, st_rf); launch_rf_synth(rf, st_rf); }
+  }
+  };
+  if (e->rf_first) launch_rf(st_rf);
   bool love_forked = false;
   if (nswd > 0 || gen.ncurves > 0) {
     { KTimer kt(e, BH_K_PREP_SWD, st);
@@ -482,26 +509,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     }
   }
   if (love_forked && e->rf_after_love && st_rf != st) st_rf = e->s_aux2;
-  for (int t = 0; t < ts.ntargets; ++t) {
-    const TargetDev& d = ts.t[t];
-    if (!is_rf(d.ref)) continue;
-    { KTimer kt(e, BH_K_PREP_RF, st_rf);
-      launch_prepare(model, nlay, rho, B, lmax, false, true, d.p, d.nsv, d.qp, d.qs, prep, st_rf); }
-    RfLaunch rf{};
-    rf.lay = prep.rf_lay; rf.coef = prep.rf_coef; rf.mc = prep.rf_mc; rf.nlay = nlay;
-    rf.B = B; rf.lmax = lmax;
-    rf.k.dw = 2.0 * RF_PI * d.fsamp / d.nsamp;
-    rf.k.wref = 2.0 * RF_PI * 1.0;
-    rf.k.a = d.gauss; rf.k.tshift = d.tshift;
-    rf.k.qn = sqrt(RF_PI) * d.fsamp / d.gauss;
-    rf.k.u = d.p * RF_DEG_PER_KM;
-    rf.k.waveno = d.waveno; rf.k.nsamp = d.nsamp;
-    rf.spec = e->spec;
-    rf.out = e->rfsynth; rf.out_stride = ts.synth_stride; rf.out_off = d.synth_off; rf.ndata = d.n;
-    rf.tstatus = e->tstatus; rf.target_id = t;
-    { KTimer kt(e, BH_K_RF_SPECTRUM, st_rf); launch_rf_spectrum(rf, st_rf); }
-    { KTimer kt(e, BH_K_RF_SYNTH, st_rf); launch_rf_synth(rf, st_rf); }
-  }
+  if (!e->rf_first) launch_rf(st_rf);
   if (st_rf != st && st_rf != e->s_aux2) {
     BH_CUDA(cudaEventRecord(e->ev_join, st_rf));
     BH_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));

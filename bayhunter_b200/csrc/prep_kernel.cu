@@ -65,7 +65,10 @@ __device__ __forceinline__ void write_rf(const RawLayer& up, const RawLayer& lo,
   (void)li;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef BH_PREP_THREADS
+#define BH_PREP_THREADS 128
+#endif
+__global__ void __launch_bounds__(BH_PREP_THREADS)
 prepare_kernel(const double* __restrict__ model, const int* __restrict__ nlay,
                const double* __restrict__ rho, int B, int lmax, int want_swd, int want_rf,
                double rf_p, double rf_nsv, double rf_qp, double rf_qs, PrepOut out) {
@@ -152,7 +155,7 @@ void launch_prepare(const double* model, const int* nlay, const double* rho, int
                     double rf_qs, PrepOut out, cudaStream_t st) {
   int total = B * lmax;
   if (total <= 0) return;
-  int threads = 128;
+  int threads = BH_PREP_THREADS;
   int blocks = (total + threads - 1) / threads;
   static bool carved = false;
   if (!carved) { bh_set_carveout(prepare_kernel); carved = true; }

@@ -11,11 +11,16 @@
 // The spectrum (B x (N/2+1) x 16 B) stays L2-resident between the two.
 #include "kernels.h"
 
+// threads per CTA of the spectrum kernel
+#ifndef BH_RF_THREADS
+#define BH_RF_THREADS 128
+#endif
+
 namespace bh {
 
 namespace {
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(BH_RF_THREADS)
 rf_spectrum_kernel(RfLaunch p) {
   const int nfreq = p.k.nsamp / 2 + 1;
   const long long total = (long long)p.B * nfreq;
@@ -89,9 +94,9 @@ void launch_rf_spectrum(const RfLaunch& p, cudaStream_t st) {
   const int nfreq = p.k.nsamp / 2 + 1;
   const long long total = (long long)p.B * nfreq;
   if (total <= 0) return;
-  const int threads = 128;
+  const int threads = BH_RF_THREADS;
   long long blocks = (total + threads - 1) / threads;
-  const long long cap = 148LL * 64;   // grid-stride beyond ~64 CTAs per SM
+  const long long cap = 148LL * 64 * (128 / BH_RF_THREADS);   // grid-stride beyond ~64 CTAs per SM
   if (blocks > cap) blocks = cap;
   static bool carved = false;
   if (!carved) { bh_set_carveout(rf_spectrum_kernel); carved = true; }
