@@ -103,3 +103,53 @@ def test_likelihood_against_synthobs_formulas(oracle):
     sign, ld = np.linalg.slogdet(C)
     logL2 = -0.5 * (n * np.log(2 * np.pi) + ld) - d.dot(np.linalg.inv(C)).dot(d) / 2
     assert np.isclose(logL, logL2, rtol=1e-9)
+
+
+def test_dispersion_oracle_against_first_principles(oracle):
+    """Pins the SURF96 restatement beyond the 4 decimals of the reference's fixtures: its phase
+    velocities must be zeros of the exact layered-medium eigenproblem (motion-stress ODE system,
+    matrix exponentials in 40-digit arithmetic, oracle/first_principles.py -- nothing in common with
+    surfdisp96.f) to within the search tolerance 1e-6 c (+ REAL*4 output rounding 6e-8), for the
+    fundamental AND the first higher mode; group velocities must equal the same finite difference of
+    EXACT roots at T/(1 +- 0.005) within what that formula does to two roots known to 1e-6 each
+    (amplification 1 / (2 * 0.005) = 100 -> 2e-4, plus the REAL*4 evaluation; bound 3e-4)."""
+    import mpmath as mp
+    from oracle import first_principles as fp
+    from bayhunter_b200 import synthetic
+    mp.mp.dps = 40
+    rng = np.random.default_rng(21)
+    periods = np.array([1.0, 4.0, 15.0, 40.0])
+    models = [(np.array([5., 23., 8., 0.]), np.array([2.7, 3.6, 3.8, 4.4]), 1.73)]
+    for k in (2, 5, 9):
+        h, vs = synthetic.draw_model(rng, k)
+        models.append((h, vs, float(rng.uniform(1.5, 2.0))))
+    worst = 0.0
+    nhigher = 0
+    for h, vs, vpvs in models:
+        vp = vs * vpvs
+        rho = vp * 0.32 + 0.77
+        for ref, sec in (("ldispph", lambda c, t: fp.love_secular(h, vs, rho, c, t)),
+                         ("rdispph", lambda c, t: fp.rayleigh_secular(h, vp, vs, rho, c, t))):
+            for mode in (1, 2):
+                x, y = oracle.surfdisp(h, vp, vs, rho, ref, periods, mode=mode)
+                assert isinstance(x, np.ndarray)
+                for t, c in zip(periods, y):
+                    if c == 0.0:          # this mode does not exist at this period
+                        continue
+                    root = fp.exact_root(lambda cc: sec(cc, t), c)
+                    assert root is not None, (ref, mode, t, c)
+                    err = abs(float(root) - c) / c
+                    worst = max(worst, err)
+                    assert err <= 1.2e-6, (ref, mode, t, c, float(root))
+                    nhigher += mode == 2
+            # group velocity: the reference's finite difference (surfdisp96.f:231-239, :306), exact roots
+            gref = {"ldispph": "ldispgr", "rdispph": "rdispgr"}[ref]
+            xg, yg = oracle.surfdisp(h, vp, vs, rho, gref, periods[1:3])
+            xp, yp = oracle.surfdisp(h, vp, vs, rho, ref, periods[1:3])
+            for t, u, c in zip(periods[1:3], yg, yp):
+                ta, tb = t / 1.005, t / 0.995
+                ca = fp.exact_root(lambda cc: sec(cc, ta), c, rel=2e-2)
+                cb = fp.exact_root(lambda cc: sec(cc, tb), c, rel=2e-2)
+                uex = (1 / mp.mpf(ta) - 1 / mp.mpf(tb)) / (1 / (ta * ca) - 1 / (tb * cb))
+                assert abs(float(uex) - u) / u <= 3e-4, (gref, t, u, float(uex))
+    assert nhigher >= 6 and worst > 0
