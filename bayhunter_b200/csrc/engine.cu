@@ -81,6 +81,15 @@ struct bh_engine {
   unsigned long long* counters = nullptr;
   int* swd_queue = nullptr;   // work-item counters of the mixed dispersion launch
   int* swd_perm = nullptr;    // [max_batch] models ordered by layer count (ragged batches)
+  // Largest layer count of the batches seen lately: read back asynchronously (never waited for) and
+  // used to size the dispersion kernel's shared-memory records for the NEXT evaluations; models that
+  // exceed it are caught by a second launch with full capacity, so a stale value is never wrong.
+  int* d_maxn = nullptr;
+  int* h_maxn = nullptr;      // pinned
+  cudaEvent_t ev_maxn = nullptr;
+  bool maxn_pending = false;
+  int last_maxn = -1;
+  int adaptive_lcap = 1;
   int sort_layers = 1;        // deal models to dispersion warps in that order
   int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
   int rf_first = 0;           // enqueue the RF kernels before the dispersion kernels
@@ -155,6 +164,8 @@ void bh_engine_destroy(bh_engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
+  if (e->ev_maxn) cudaEventDestroy(e->ev_maxn);
+  if (e->h_maxn) cudaFreeHost(e->h_maxn);
   if (e->s_own) cudaStreamDestroy(e->s_own);
   if (e->s_aux) cudaStreamDestroy(e->s_aux);
   if (e->s_aux2) cudaStreamDestroy(e->s_aux2);
@@ -265,6 +276,10 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
   if (rc == BH_OK) rc = scratch(e, &e->counters, BH_NUM_COUNTERS);
   if (rc == BH_OK) rc = scratch(e, &e->swd_queue, 2 + 1024);
   if (rc == BH_OK) rc = scratch(e, &e->swd_perm, B);
+  if (rc == BH_OK) rc = scratch(e, &e->d_maxn, 1);
+  if (rc == BH_OK && (cudaMallocHost((void**)&e->h_maxn, sizeof(int)) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&e->ev_maxn, cudaEventDisableTiming) != cudaSuccess))
+    rc = set_err(BH_ERR_CUDA, "pinned readback buffer");
   if (rc == BH_OK) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -322,6 +337,9 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
     e->rf_first = value ? 1 : 0;
   } else if (!strcmp(key, "rf_after_love")) {
     e->rf_after_love = value ? 1 : 0;
+  } else if (!strcmp(key, "swd_adaptive_capacity")) {
+    e->adaptive_lcap = value ? 1 : 0;
+    e->last_maxn = -1;
   } else if (!strcmp(key, "swd_sort_layers")) {
     e->sort_layers = value ? 1 : 0;
   } else if (!strcmp(key, "swd_split_waves")) {
@@ -435,9 +453,20 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   if (e->rf_first) launch_rf(st_rf);
   bool love_forked = false;
   if (nswd > 0 || gen.ncurves > 0) {
+    // record capacity of the main dispersion launch: the layer counts seen lately (+2), not lmax
+    int cap = lmax;
+    if (e->adaptive_lcap && e->sort_layers && nswd > 0) {
+      if (e->maxn_pending && cudaEventQuery(e->ev_maxn) == cudaSuccess) {
+        e->last_maxn = *e->h_maxn;
+        e->maxn_pending = false;
+      }
+      if (e->last_maxn > 0 && e->last_maxn + 2 < lmax) cap = e->last_maxn + 2;
+    }
     { KTimer kt(e, BH_K_PREP_SWD, st);
       launch_prepare(model, nlay, rho, B, lmax, true, false, 0, 0, 0, 0, prep, st);
-      if (e->sort_layers && nswd > 0) launch_layer_order(nlay, B, e->swd_perm, nullptr, st); }
+      if (e->sort_layers && nswd > 0) {
+        launch_layer_order(nlay, B, e->swd_perm, e->d_maxn, st);
+      } }
     // models per warp: phase curves S (one chain per model), group curves S_g <= 16
     // (two chains per model).  Fewer models per warp = more spare lanes for bracket
     // speculation = fewer rounds, but more warps to issue.  Measured on B200
@@ -462,8 +491,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     if (Sg == 0) Sg = S > 16 ? 16 : S;
     if (Sg > 16) Sg = 16;
     // keep one warp's records + mailbox within ~24 KB of shared memory
-    while (S > 1 && swd_smem_bytes(lmax, S) > 24 * 1024) S >>= 1;
-    while (Sg > 1 && swd_smem_bytes(lmax, Sg) > 24 * 1024) Sg >>= 1;
+    auto fit = [](int s_, int lc) { while (s_ > 1 && swd_smem_bytes(lc, s_) > 24 * 1024) s_ >>= 1; return s_; };
     if (swl[0].ncurves > 0 && swl[1].ncurves > 0 && e->concurrent) {
       // Love chains share the SMs with the Rayleigh chains: own stream, forked after
       // the row preparation and before the Rayleigh launch
@@ -478,34 +506,49 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       sw.perm = e->sort_layers ? e->swd_perm : nullptr;
       sw.curves = e->curves; sw.roots = e->roots; sw.curve_stride = e->curve_stride;
       sw.tstatus = e->tstatus; sw.counters = e->counters;
-      sw.lcap = lmax;
-      for (int c = 0; c < sw.ncurves; ++c) {
-        sw.spw[c] = sw.igr[c] ? Sg : S;
-        const int ov = e->spw_curve[(sw.wave[c] == 2 ? 0 : 2) + (sw.igr[c] ? 0 : 1)];
-        if (ov > 0) {
-          sw.spw[c] = ov;
-          while (sw.spw[c] > 1 && swd_smem_bytes(lmax, sw.spw[c]) > 24 * 1024) sw.spw[c] >>= 1;
-        }
-      }
       sw.max_spec = e->max_spec;
-      sw.direct = (e->direct == 2 || (e->direct == 1 && S == 32 && Sg == 16)) ? 1 : 0;
       cudaStream_t sst = st;
       if (w == 1 && love_forked) sst = e->s_aux2;
       bool mixed = false;
       for (int c = 1; c < sw.ncurves; ++c) mixed |= sw.wave[c] != sw.wave[0];
-      if (mixed && e->rayleigh_sm_pct > 0 && e->nsm > 1 && e->nsm <= 1024) {
-        // dedicate SMs [0, split) to the Rayleigh items, the rest to the Love items
-        long long wr = 0, wl = 0;
-        for (int c = 0; c < sw.ncurves; ++c) (sw.wave[c] == 2 ? wr : wl) += (B + sw.spw[c] - 1) / sw.spw[c];
-        int split = (e->nsm * e->rayleigh_sm_pct / 100) & ~1;      // whole TPCs
-        if (split < 2) split = 2;
-        if (split > e->nsm - 2) split = e->nsm - 2;
-        sw.queue = e->swd_queue; sw.sm_split = split;
-        sw.type_quota[0] = (int)((wr + split - 1) / split);
-        sw.type_quota[1] = (int)((wl + (e->nsm - split) - 1) / (e->nsm - split));
-        BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
+      // pass 0: models with at most `cap` rows, records sized for cap; pass 1 (only when cap < lmax):
+      // the deeper models with full capacity.  Warps of pass 1 without such a model exit at once.
+      for (int pass = 0; pass < (cap < lmax ? 2 : 1); ++pass) {
+        const int lc = pass == 0 ? cap : lmax;
+        sw.lcap = lc;
+        sw.nlay_lo = pass == 0 ? -1 : cap;
+        sw.nlay_hi = (pass == 0 && cap < lmax) ? cap : 0x7fffffff;
+        for (int c = 0; c < sw.ncurves; ++c) {
+          sw.spw[c] = fit(sw.igr[c] ? Sg : S, lc);
+          const int ov = e->spw_curve[(sw.wave[c] == 2 ? 0 : 2) + (sw.igr[c] ? 0 : 1)];
+          if (ov > 0) sw.spw[c] = fit(ov, lc);
+        }
+        bool full = true;
+        for (int c = 0; c < sw.ncurves; ++c) full = full && sw.spw[c] == (sw.igr[c] ? 16 : 32);
+        sw.direct = (e->direct == 2 || (e->direct == 1 && full)) ? 1 : 0;
+        sw.queue = nullptr;
+        if (pass == 0 && mixed && e->rayleigh_sm_pct > 0 && e->nsm > 1 && e->nsm <= 1024) {
+          // dedicate SMs [0, split) to the Rayleigh items, the rest to the Love items
+          long long wr = 0, wl = 0;
+          for (int c = 0; c < sw.ncurves; ++c) (sw.wave[c] == 2 ? wr : wl) += (B + sw.spw[c] - 1) / sw.spw[c];
+          int split = (e->nsm * e->rayleigh_sm_pct / 100) & ~1;      // whole TPCs
+          if (split < 2) split = 2;
+          if (split > e->nsm - 2) split = e->nsm - 2;
+          sw.queue = e->swd_queue; sw.sm_split = split;
+          sw.type_quota[0] = (int)((wr + split - 1) / split);
+          sw.type_quota[1] = (int)((wl + (e->nsm - split) - 1) / (e->nsm - split));
+          BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
+        }
+        if (pass == 0) { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
+        else launch_swd(sw, sst);
       }
-      { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
+    }
+    if (e->adaptive_lcap && e->sort_layers && nswd > 0) {
+      // read the batch's largest layer count back behind the dispersion kernel (for LATER evaluations;
+      // enqueued after the launch so that it cannot delay it)
+      BH_CUDA(cudaMemcpyAsync(e->h_maxn, e->d_maxn, sizeof(int), cudaMemcpyDeviceToHost, st));
+      BH_CUDA(cudaEventRecord(e->ev_maxn, st));
+      e->maxn_pending = true;
     }
   }
   if (love_forked && e->rf_after_love && st_rf != st) st_rf = e->s_aux2;
@@ -663,6 +706,7 @@ int bh_surfdisp96(const float* thkm, const float* vpm, const float* vsm, const f
     sw.target_id[0] = 0; sw.wave[0] = iwave; sw.igr[0] = igr > 0 ? 1 : 0; sw.kmax[0] = kmax;
     sw.periods[0] = s.periods; sw.curves = s.curve; sw.roots = s.roots; sw.curve_stride = BH_MAX_PERIODS; sw.curve_off[0] = 0;
     sw.tstatus = s.tstatus; sw.counters = nullptr; sw.spw[0] = 1; sw.lcap = nlayer; sw.max_spec = 32; sw.direct = 0;
+    sw.nlay_lo = -1; sw.nlay_hi = 0x7fffffff;
     launch_swd(sw, s.st);
   }
   int ok = 0;

@@ -69,8 +69,8 @@ void launch_prepare(const double* model, const int* nlay, const double* rho, int
                     bool want_swd, bool want_rf, double rf_p, double rf_nsv, double rf_qp,
                     double rf_qs, PrepOut out, cudaStream_t st);
 // perm[B]: model indices ordered by decreasing layer count (counting sort; order within a layer
-// count is arbitrary).  scratch: int[2 * 128], zeroed by the call.
-void launch_layer_order(const int* nlay, int B, int* perm, int* scratch, cudaStream_t st);
+// count is arbitrary).  *maxn (device, may be null) receives the largest layer count.
+void launch_layer_order(const int* nlay, int B, int* perm, int* maxn, cudaStream_t st);
 // explicit single-model arrays for the synrf shim (z, vp, vs, rho, qp, qs as given)
 void launch_prepare_rf_explicit(const double* z, const double* vp, const double* vs,
                                 const double* rho, const double* qp, const double* qs, int nlay,
@@ -80,7 +80,8 @@ void launch_prepare_rf_explicit(const double* z, const double* vp, const double*
 struct SwdLaunch {
   const LayerRow* rows;         // [B][row_stride] REAL*4 rows (d, vp, vs, rho)
   int row_stride;
-  int lcap;                     // layer capacity of the shared-memory records (>= max nlay)
+  int lcap;                     // layer capacity of the shared-memory records (>= nlay_hi)
+  int nlay_lo, nlay_hi;         // models with nlay in (nlay_lo, nlay_hi] belong to this launch
   const int* nlay;
   const int* perm;              // [B] order in which models are dealt to warps (null: 0, 1, 2, ...)
   int B;

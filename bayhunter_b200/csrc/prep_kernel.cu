@@ -123,7 +123,7 @@ __global__ void prepare_rf_explicit_kernel(const double* __restrict__ z, const d
 
 // Counting sort of the models by layer count, longest first: one CTA; the bins live in shared memory.
 __global__ void __launch_bounds__(1024)
-layer_order_kernel(const int* __restrict__ nlay, int B, int* __restrict__ perm) {
+layer_order_kernel(const int* __restrict__ nlay, int B, int* __restrict__ perm, int* __restrict__ maxn) {
   __shared__ int hist[128], start[128];
   const int t = threadIdx.x;
   if (t < 128) hist[t] = 0;
@@ -134,8 +134,9 @@ layer_order_kernel(const int* __restrict__ nlay, int B, int* __restrict__ perm) 
   }
   __syncthreads();
   if (t == 0) {
-    int acc = 0;
-    for (int n = 127; n >= 0; --n) { start[n] = acc; acc += hist[n]; }
+    int acc = 0, mx = 0;
+    for (int n = 127; n >= 0; --n) { start[n] = acc; acc += hist[n]; if (hist[n] && n > mx) mx = n; }
+    if (maxn) *maxn = mx;
   }
   __syncthreads();
   for (int b = t; b < B; b += blockDim.x) {
@@ -144,10 +145,9 @@ layer_order_kernel(const int* __restrict__ nlay, int B, int* __restrict__ perm) 
   }
 }
 
-void launch_layer_order(const int* nlay, int B, int* perm, int* scratch, cudaStream_t st) {
-  (void)scratch;
+void launch_layer_order(const int* nlay, int B, int* perm, int* maxn, cudaStream_t st) {
   if (B <= 0) return;
-  layer_order_kernel<<<1, 1024, 0, st>>>(nlay, B, perm);
+  layer_order_kernel<<<1, 1024, 0, st>>>(nlay, B, perm, maxn);
 }
 
 void launch_prepare(const double* model, const int* nlay, const double* rho, int B, int lmax,

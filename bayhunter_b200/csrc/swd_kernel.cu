@@ -122,7 +122,15 @@ swd_kernel(SwdLaunch p) {
   //      [S, S + nsearch) the second-root chains of group curves (role B) ----
   const int role = (igr > 0 && lane >= S) ? 1 : 0;
   const int sidx = role ? lane - S : lane;            // model slot within the warp
-  const bool owner = sidx < nsearch && (role == 0 || igr > 0) && lane < (igr > 0 ? 2 * S : S);
+  bool owner = sidx < nsearch && (role == 0 || igr > 0) && lane < (igr > 0 ? 2 * S : S);
+  // This launch takes the models whose row count lies in (nlay_lo, nlay_hi]: the record
+  // capacity `lcap` follows the layer counts seen lately, deeper models go to a second launch
+  // with full capacity (engine.cu).  Warps without a model in range leave at once.
+  if (owner) {
+    const int n = p.nlay[BH_MODEL(sidx)];
+    owner = n > p.nlay_lo && n <= p.nlay_hi;
+  }
+  if (!__any_sync(0xffffffffu, owner)) return;
   Search s;
   SearchCtx ctx;
   ctx.omA = ws->omA; ctx.omB = ws->omB;
@@ -153,7 +161,7 @@ swd_kernel(SwdLaunch p) {
   for (int t = lane; t < lcap * S; t += 32) {
     const int m = t % S, l = t / S;
     if (m < nsearch) {
-      const int L = ws->nlay[m];
+      const int L = ws->nlay[m];                      // 0 for slots outside this launch's range
       if (l < L) {
         const LayerRow r = p.rows[(size_t)BH_MODEL(m) * stride + l];
         swd_make_rec(wave, r, l == L - 1, rec + (size_t)l * S + m, fs);

@@ -426,3 +426,32 @@ def test_synthobs_reproduces_tutorial_observed_files(golden_dir, tmp_path):
         assert np.allclose(got[:, 0], want[:, 0], atol=1e-4)
         assert np.abs(got[:, 1] - want[:, 1]).max() <= 1.01e-4, ref      # both sides printed with 4 decimals
     assert open(tmp_path / "st3_mod.dat").read().split() == open(golden_dir + "/st3_mod.dat").read().split()
+
+
+def test_adaptive_record_capacity_never_changes_results():
+    """The dispersion kernel sizes its shared-memory layer records by the layer counts of RECENT
+    batches; a batch with deeper models than that must be caught by the second (full-capacity)
+    launch.  Same results, bit for bit, as with the feature off."""
+    import torch
+    from bayhunter_b200 import Engine, TargetSpec, synthetic
+    rng = np.random.default_rng(3)
+    periods = np.linspace(1, 40, 16)
+    specs = [TargetSpec(r, periods, 3.5 + rng.normal(0, .1, 16), cov="exp") for r in ("rdispph", "rdispgr", "ldispph")]
+    B, lmax = 192, 20
+    shallow, n_sh = synthetic.draw_batch(B, (2, 5), seed=1, lmax=lmax)
+    deep, n_dp = synthetic.draw_batch(B, (2, 19), seed=2, lmax=lmax)
+    noise = synthetic.draw_noise(B, [s.ref for s in specs], seed=3)
+    ref_eng = Engine(specs, B, lmax)
+    ref_eng.set(swd_adaptive_capacity=0)
+    want_sh = ref_eng.eval_host(shallow, n_sh, noise, want_synth=True)
+    want_dp = ref_eng.eval_host(deep, n_dp, noise, want_synth=True)
+    eng = Engine(specs, B, lmax)
+    for _ in range(3):                       # lets the read-back of the layer count land
+        got_sh = eng.eval_host(shallow, n_sh, noise, want_synth=True)
+        torch.cuda.synchronize()
+    got_dp = eng.eval_host(deep, n_dp, noise, want_synth=True)      # capacity is now 7 rows: 2 launches
+    got_sh2 = eng.eval_host(shallow, n_sh, noise, want_synth=True)
+    for got, want in ((got_sh, want_sh), (got_dp, want_dp), (got_sh2, want_sh)):
+        assert np.array_equal(got[2], want[2])
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[3], want[3], equal_nan=True)
+    assert want_dp[2].mean() > 0.5 and (n_dp > 7).sum() > B // 2
