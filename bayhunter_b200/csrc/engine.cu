@@ -90,6 +90,15 @@ struct bh_engine {
   bool maxn_pending = false;
   int last_maxn = -1;
   int adaptive_lcap = 1;
+  // models-per-warp autotuning ("swd_autotune"): candidates around the rule's pick, timed in place
+  struct Tune {
+    int B = -1, base = -1, ncand = 0, cur = 0, locked = -1;
+    int cand[3] = {0, 0, 0}, trials[3] = {0, 0, 0};
+    float best_ms[3] = {0.f, 0.f, 0.f};
+    bool pending = false;
+  } tune;
+  int autotune = 0;
+  cudaEvent_t ev_tune[2] = {nullptr, nullptr};
   int sort_layers = 1;        // deal models to dispersion warps in that order
   int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
   int rf_first = 0;           // enqueue the RF kernels before the dispersion kernels
@@ -165,6 +174,7 @@ void bh_engine_destroy(bh_engine* e) {
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->ev_maxn) cudaEventDestroy(e->ev_maxn);
+  for (cudaEvent_t ev : e->ev_tune) if (ev) cudaEventDestroy(ev);
   if (e->h_maxn) cudaFreeHost(e->h_maxn);
   if (e->s_own) cudaStreamDestroy(e->s_own);
   if (e->s_aux) cudaStreamDestroy(e->s_aux);
@@ -337,6 +347,13 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
     e->rf_first = value ? 1 : 0;
   } else if (!strcmp(key, "rf_after_love")) {
     e->rf_after_love = value ? 1 : 0;
+  } else if (!strcmp(key, "swd_autotune")) {
+    e->autotune = value ? 1 : 0;
+    e->tune = bh_engine::Tune();
+    if (e->autotune && !e->ev_tune[0]) {
+      BH_CUDA(cudaEventCreate(&e->ev_tune[0]));
+      BH_CUDA(cudaEventCreate(&e->ev_tune[1]));
+    }
   } else if (!strcmp(key, "swd_adaptive_capacity")) {
     e->adaptive_lcap = value ? 1 : 0;
     e->last_maxn = -1;
@@ -469,21 +486,59 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       } }
     // models per warp: phase curves S (one chain per model), group curves S_g <= 16
     // (two chains per model).  Fewer models per warp = more spare lanes for bracket
-    // speculation = fewer rounds, but more warps to issue.  Measured on B200
-    // (profiles/r01_swd_sweep.txt): ~2048 warps are best when there are enough chains
-    // to fill them (>= 32768), ~1024 warps below that.
+    // speculation = fewer rounds, but more warps to issue.  Rule fitted to sweeps on B200
+    // (profiles/r01_swd_sweep.txt, r01_variants.txt): about 14 chains per warp until one resident
+    // wave (~2400 warps) is full.  With "swd_autotune" the neighbours of that pick are timed on the
+    // first evaluations (events, never waited for) and the fastest is kept: results do not depend
+    // on the choice, only the time does.
     int S = e->searches_per_warp, Sg = e->group_spw;
+    bool tuning_now = false;
     if (S == 0) {
       long long nph = 0, ngr = 0;
       for (int w = 0; w < 2; ++w)
         for (int c = 0; c < swl[w].ncurves; ++c) (swl[w].igr[c] ? ngr : nph) += 1;
       const long long chains = (long long)B * (nph + 2 * ngr);
-      const long long target = chains >= 32768 ? 2048 : 1024;
+      long long target = chains / 14;
+      if (target > 2400) target = 2400;
       static const int cand[][2] = {{32, 16}, {16, 16}, {16, 8}, {8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {2, 1}, {1, 1}};
       int pick = 9;
+      long long bestd = -1;
       for (int i = 0; i < 10; ++i) {
         const long long warps = nph * ((B + cand[i][0] - 1) / cand[i][0]) + ngr * ((B + cand[i][1] - 1) / cand[i][1]);
-        if (warps >= target) { pick = i; break; }
+        const long long d = warps > target ? warps - target : target - warps;
+        if (bestd < 0 || d < bestd) { bestd = d; pick = i; }
+      }
+      if (e->autotune && Sg == 0) {
+        bh_engine::Tune& t = e->tune;
+        if (t.B != B || t.base != pick) {              // new problem size: start over
+          t = bh_engine::Tune();
+          t.B = B; t.base = pick;
+          for (int i = pick - 1; i <= pick + 1; ++i) if (i >= 0 && i < 10) t.cand[t.ncand++] = i;
+        }
+        if (t.locked < 0) {
+          if (t.pending && cudaEventQuery(e->ev_tune[1]) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e->ev_tune[0], e->ev_tune[1]) == cudaSuccess) {
+              if (t.trials[t.cur] == 0 || ms < t.best_ms[t.cur]) t.best_ms[t.cur] = ms;
+              t.trials[t.cur] += 1;
+            }
+            t.pending = false;
+            int next = -1;
+            for (int k = 1; k <= t.ncand; ++k) {       // round robin over candidates short of 3 timings
+              const int j = (t.cur + k) % t.ncand;
+              if (t.trials[j] < 3) { next = j; break; }
+            }
+            if (next < 0) {
+              int b = 0;
+              for (int j = 1; j < t.ncand; ++j) if (t.best_ms[j] < t.best_ms[b]) b = j;
+              t.locked = t.cand[b];
+            } else {
+              t.cur = next;
+            }
+          }
+          if (t.locked < 0) { pick = t.cand[t.cur]; tuning_now = !t.pending; }
+        }
+        if (t.locked >= 0) pick = t.locked;
       }
       S = cand[pick][0];
       if (Sg == 0) Sg = cand[pick][1];
@@ -499,6 +554,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       BH_CUDA(cudaStreamWaitEvent(e->s_aux2, e->ev_fork2, 0));
       love_forked = true;
     }
+    if (tuning_now) BH_CUDA(cudaEventRecord(e->ev_tune[0], st));
     for (int w = 0; w < 2; ++w) {
       SwdLaunch& sw = swl[w];
       if (sw.ncurves == 0) continue;
@@ -542,6 +598,14 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
         if (pass == 0) { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
         else launch_swd(sw, sst);
       }
+    }
+    if (tuning_now) {
+      if (love_forked) {                               // the Love launch is part of what is timed
+        BH_CUDA(cudaEventRecord(e->ev_join2, e->s_aux2));
+        BH_CUDA(cudaStreamWaitEvent(st, e->ev_join2, 0));
+      }
+      BH_CUDA(cudaEventRecord(e->ev_tune[1], st));
+      e->tune.pending = true;
     }
     if (e->adaptive_lcap && e->sort_layers && nswd > 0) {
       // read the batch's largest layer count back behind the dispersion kernel (for LATER evaluations;

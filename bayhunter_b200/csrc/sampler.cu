@@ -260,6 +260,7 @@ int bh_sampler_create(bh_engine* e, const bh_sampler_config* c, int ntargets, in
   s->eng = e; s->B = nchains; s->S = c->max_accepted; s->T = ntargets; s->maxl = c->layers_max + 1;
   s->first_chain = first_chain;
   s->cfg = sampler_cfg_from_public(*c, ntargets);
+  bh_engine_set(e, "swd_autotune", 1);     // a sampler evaluates the same batch size thousands of times
   const size_t B = (size_t)nchains, L = (size_t)s->maxl, T = (size_t)ntargets, S = (size_t)s->S;
   int rc = BH_OK;
 #define A(p, n) if (rc == BH_OK) rc = salloc(s, &s->p, (n))

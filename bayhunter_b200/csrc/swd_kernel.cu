@@ -23,11 +23,17 @@
 #include "kernels.h"
 
 // resident warps (= CTAs) per SM the register allocation must allow
-// 14: the compiler fits the Rayleigh instantiations into 128 registers without spilling, so the
-// whole grid of a batch (~2048 warps) is resident at once instead of leaving a second wave
-// (measured: dispersion kernel 4.65 -> 4.2 ms alone, profiles/r01_variants.txt)
+// Register budget of the instantiations that carry the Rayleigh code, as "resident warps (= CTAs)
+// per SM the allocation must allow":
+//   12 -> 147 registers: the faster code (~10 %) whenever the whole grid is resident anyway
+//   14 -> 128 registers, no spills: the whole grid of a full batch (~2048 warps on 148 SMs) is
+//         resident at once instead of leaving a second wave (4.65 -> 4.2 ms at B = 8192)
+// launch_one() picks per launch from the grid size (profiles/r01_variants.txt).
 #ifndef BH_SWD_MIN_BLOCKS_RAYLEIGH
-#define BH_SWD_MIN_BLOCKS_RAYLEIGH 14
+#define BH_SWD_MIN_BLOCKS_RAYLEIGH 12
+#endif
+#ifndef BH_SWD_MIN_BLOCKS_RAYLEIGH_DENSE
+#define BH_SWD_MIN_BLOCKS_RAYLEIGH_DENSE 14
 #endif
 #ifndef BH_SWD_MIN_BLOCKS_LOVE
 #define BH_SWD_MIN_BLOCKS_LOVE 16
@@ -68,8 +74,8 @@ __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
 // kWave: 1 Love, 2 Rayleigh -- one instantiation per wave type, so that the Love
 // chains do not pay for the Rayleigh code's registers; the two are launched on
 // different streams and share the SMs.
-template <bool kDirect, int kWave>
-__global__ void __launch_bounds__(32, kWave == 1 ? BH_SWD_MIN_BLOCKS_LOVE : BH_SWD_MIN_BLOCKS_RAYLEIGH)
+template <bool kDirect, int kWave, int kMinBlocks>
+__global__ void __launch_bounds__(32, kMinBlocks)
 swd_kernel(SwdLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
@@ -290,26 +296,40 @@ size_t swd_smem_bytes(int lcap, int S) {
   return (size_t)SWD_REC_FIELDS * lcap * S * sizeof(double) + sizeof(WarpShared);
 }
 
-template <bool kDirect, int kWave>
-static void launch_one(const SwdLaunch& p, int warps, size_t smem, cudaStream_t st) {
+template <bool kDirect, int kWave, int kMinBlocks>
+static void launch_inst(const SwdLaunch& p, int warps, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   static bool carved = false;
-  if (!carved) { bh_set_carveout(swd_kernel<kDirect, kWave>); carved = true; }
+  if (!carved) { bh_set_carveout(swd_kernel<kDirect, kWave, kMinBlocks>); carved = true; }
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(swd_kernel<kDirect, kWave>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(swd_kernel<kDirect, kWave, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
   static bool reported = false;
   if (!reported && getenv("BH_DEBUG")) {
     reported = true;
     int nb = -1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, swd_kernel<kDirect, kWave>, 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, swd_kernel<kDirect, kWave, kMinBlocks>, 32, smem);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, swd_kernel<kDirect, kWave>);
-    fprintf(stderr, "[bh] swd_kernel<%d,%d>: %d warps, smem %zu B, regs %d, local %zu B, carveout %d, max resident CTAs/SM %d\n",
-            (int)kDirect, kWave, warps, smem, fa.numRegs, fa.localSizeBytes, fa.preferredShmemCarveout, nb);
+    cudaFuncGetAttributes(&fa, swd_kernel<kDirect, kWave, kMinBlocks>);
+    fprintf(stderr, "[bh] swd_kernel<%d,%d,%d>: %d warps, smem %zu B, regs %d, local %zu B, carveout %d, max resident CTAs/SM %d\n",
+            (int)kDirect, kWave, kMinBlocks, warps, smem, fa.numRegs, fa.localSizeBytes, fa.preferredShmemCarveout, nb);
   }
-  swd_kernel<kDirect, kWave><<<warps, 32, smem, st>>>(p);
+  swd_kernel<kDirect, kWave, kMinBlocks><<<warps, 32, smem, st>>>(p);
+}
+
+template <bool kDirect, int kWave>
+static void launch_one(const SwdLaunch& p, int warps, size_t smem, cudaStream_t st) {
+  if (kWave == 1) { launch_inst<kDirect, 1, BH_SWD_MIN_BLOCKS_LOVE>(p, warps, smem, st); return; }
+  static int nsm = 0;
+  if (nsm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 1) nsm = 148;
+  }
+  // the roomy build holds 13 warps per SM; a larger grid takes the 128-register build
+  if (warps > 13 * nsm) launch_inst<kDirect, kWave, BH_SWD_MIN_BLOCKS_RAYLEIGH_DENSE>(p, warps, smem, st);
+  else launch_inst<kDirect, kWave, BH_SWD_MIN_BLOCKS_RAYLEIGH>(p, warps, smem, st);
 }
 
 // Curves of one wave type run the specialised instantiation; a mixed set of curves

@@ -117,6 +117,9 @@ int bh_engine_synth_stride(const bh_engine* e);
  *   key "swd_adaptive_capacity"  0/1     size the dispersion kernel's per-warp layer records by the layer
  *                                        counts of recent batches instead of lmax; deeper models are
  *                                        handled by a second launch (default 1; results do not depend on it)
+ *   key "swd_autotune"           0/1     time the neighbours of the models-per-warp rule's pick on the
+ *                                        first evaluations of a batch size and keep the fastest (default 0;
+ *                                        the device sampler switches it on; results do not depend on it)
  *   key "swd_direct"             0/1/2   chains evaluate only their own candidate: never (default) /
  *                                        when warps are full of chains / always
  *   key "swd_rayleigh_sm_pct"    0..100  one launch: share of the SMs whose CTAs take the Rayleigh work
