@@ -102,6 +102,9 @@ struct bh_engine {
   int sort_layers = 1;        // deal models to dispersion warps in that order
   int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
   int rf_first = 0;           // enqueue the RF kernels before the dispersion kernels
+  // Spectral bins whose Gauss-filter weight exp(-(w/2a)^2) is below this are not computed: next to a
+  // trace peak of order 0.1-1 they are below the resolution of fp64 (1e-30 vs 2e-16).  0 = all bins.
+  double rf_floor = 1e-30;
   int nsm = 0;
   int max_nfreq = 0;
   // device mirrors for the host-pointer entry point
@@ -343,6 +346,10 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "swd_rayleigh_sm_pct")) {
     if (value < 0 || value > 100) return set_err(BH_ERR_ARG, "swd_rayleigh_sm_pct must be 0..100");
     e->rayleigh_sm_pct = value;
+  } else if (!strcmp(key, "rf_prune_exp10")) {
+    // bins with a Gauss weight below 10^-value are skipped; 0 disables the pruning
+    if (value < 0 || value > 300) return set_err(BH_ERR_ARG, "rf_prune_exp10 must be 0 (off) or 1..300");
+    e->rf_floor = value ? pow(10.0, -(double)value) : 0.0;
   } else if (!strcmp(key, "rf_first")) {
     e->rf_first = value ? 1 : 0;
   } else if (!strcmp(key, "rf_after_love")) {
@@ -461,6 +468,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     rf.k.u = d.p * RF_DEG_PER_KM;
     rf.k.waveno = d.waveno; rf.k.nsamp = d.nsamp;
     rf.spec = e->spec;
+    rf.nact = rf_active_frequencies(rf.k, e->rf_floor);
     rf.out = e->rfsynth; rf.out_stride = ts.synth_stride; rf.out_off = d.synth_off; rf.ndata = d.n;
     rf.tstatus = e->tstatus; rf.target_id = t;
     { KTimer kt(e, BH_K_RF_SPECTRUM, st_rf); launch_rf_spectrum(rf, st_rf); }
@@ -816,7 +824,7 @@ int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a, double 
   rfl.lay = s.rf_lay; rfl.coef = s.rf_coef; rfl.mc = s.rf_mc; rfl.nlay = s.nlay; rfl.B = 1; rfl.lmax = nlay;
   rfl.k.dw = 2.0 * RF_PI * fsamp / nsamp; rfl.k.wref = 2.0 * RF_PI; rfl.k.a = a; rfl.k.tshift = tshift;
   rfl.k.qn = sqrt(RF_PI) * fsamp / a; rfl.k.u = p * RF_DEG_PER_KM; rfl.k.waveno = waveno; rfl.k.nsamp = nsamp;
-  rfl.spec = s.spec; rfl.out = s.trace; rfl.out_stride = nsamp; rfl.out_off = 0; rfl.ndata = nsamp;
+  rfl.spec = s.spec; rfl.nact = rf_active_frequencies(rfl.k, 1e-30); rfl.out = s.trace; rfl.out_stride = nsamp; rfl.out_off = 0; rfl.ndata = nsamp;
   rfl.tstatus = nullptr; rfl.target_id = 0;
   launch_rf_spectrum(rfl, s.st);
   launch_rf_synth(rfl, s.st);

@@ -140,11 +140,16 @@ struct RfLaunch {
   int B, lmax;
   RfSpecConsts k;
   cd* spec;          // [B][nfreq]
+  int nact;          // frequencies 0 .. nact-1 are computed; the Gauss filter makes the rest exactly
+                     // negligible (engine.cu: rf_active_frequencies), they enter the transform as 0
   double* out;       // [B][out_stride] time series written at out_off, first ndata samples
   int out_stride, out_off, ndata;
   int* tstatus;      // [B][kMaxTargets]
   int target_id;
 };
+// Number of leading frequency bins whose Gauss weight exp(-(w/2a)^2) is >= floor (0 < floor < 1;
+// floor <= 0: all nsamp/2+1 bins).
+int rf_active_frequencies(const RfSpecConsts& k, double wfloor);
 void launch_rf_spectrum(const RfLaunch& p, cudaStream_t st);
 void launch_rf_synth(const RfLaunch& p, cudaStream_t st);
 

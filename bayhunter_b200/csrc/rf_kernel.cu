@@ -23,12 +23,14 @@ namespace {
 __global__ void __launch_bounds__(BH_RF_THREADS)
 rf_spectrum_kernel(RfLaunch p) {
   const int nfreq = p.k.nsamp / 2 + 1;
-  const long long total = (long long)p.B * nfreq;
+  const int nact = p.nact;                       // bins that matter (rf_active_frequencies)
+  const long long total = (long long)p.B * nact;
   const double u2 = p.k.u * p.k.u;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(idx / nfreq);
-    const int j = (int)(idx - (long long)b * nfreq);
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(it / nact);
+    const int j = (int)(it - (long long)b * nact);
+    const long long idx = (long long)b * nfreq + j;
     int nl = p.nlay[b];
     if (nl > p.lmax) nl = p.lmax;
     cd out = mk(NAN, NAN);
@@ -60,19 +62,28 @@ __global__ void rf_synth_kernel(RfLaunch p) {
   int logn = 0;
   while ((1 << logn) < N) ++logn;
   // Hermitian extension + bit reversal (iftr, greens.cpp:149-152)
+  const int nact = p.nact;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    cd v = (i <= N / 2) ? spec[i] : cconj(spec[N - i]);
+    const int k = (i <= N / 2) ? i : N - i;
+    cd v = mk(0.0, 0.0);
+    if (k < nact) v = (i <= N / 2) ? spec[k] : cconj(spec[k]);
     int r = (int)(__brev((unsigned)i) >> (32 - logn));
     x[r] = v;
   }
+  // twiddles exp(+i pi k / (N/2)), k < N/2, once per CTA (the reference recomputes exp() inside
+  // its butterfly loops, fork.cpp:40-55; same values)
+  cd* tw = x + N;
+  for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
+    double sw, cw;
+    sincospi((double)k / (double)(N / 2), &sw, &cw);
+    tw[k] = mk(cw, sw);
+  }
   __syncthreads();
-  for (int l = 1; l < N; l <<= 1) {
+  for (int l = 1, sh = logn - 1; l < N; l <<= 1, --sh) {
     for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
       int m = t & (l - 1);
       int i = ((t - m) << 1) + m;
-      double sw, cw;
-      sincospi((double)m / (double)l, &sw, &cw);
-      cd wv = mk(cw, sw);
+      cd wv = tw[m << sh];                      // exp(i pi m / l) = tw[m * (N/2) / l]
       cd a = x[i], bb = wv * x[i + l];
       x[i] = a + bb;
       x[i + l] = a - bb;
@@ -90,9 +101,18 @@ __global__ void rf_synth_kernel(RfLaunch p) {
 
 }  // namespace
 
+int rf_active_frequencies(const RfSpecConsts& k, double wfloor) {
+  const int nfreq = k.nsamp / 2 + 1;
+  if (!(wfloor > 0.0) || !(wfloor < 1.0) || !(k.a > 0.0) || !(k.dw > 0.0)) return nfreq;
+  // exp(-0.25 (w/a)^2) >= floor  <=>  w <= 2 a sqrt(-ln floor); the reference clips w/a at 50
+  // (greens.cpp:386), far above any floor that is not denormal
+  const double wmax = 2.0 * k.a * sqrt(-log(wfloor));
+  const double j = floor(wmax / k.dw) + 2.0;     // one bin of slack
+  return j < (double)nfreq ? (int)j : nfreq;
+}
+
 void launch_rf_spectrum(const RfLaunch& p, cudaStream_t st) {
-  const int nfreq = p.k.nsamp / 2 + 1;
-  const long long total = (long long)p.B * nfreq;
+  const long long total = (long long)p.B * p.nact;
   if (total <= 0) return;
   const int threads = BH_RF_THREADS;
   long long blocks = (total + threads - 1) / threads;
@@ -109,7 +129,7 @@ void launch_rf_synth(const RfLaunch& p, cudaStream_t st) {
   int threads = N / 2;
   if (threads > 512) threads = 512;
   if (threads < 32) threads = 32;
-  const size_t smem = sizeof(cd) * (size_t)N;
+  const size_t smem = sizeof(cd) * ((size_t)N + (size_t)N / 2);     // samples + twiddles
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(rf_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

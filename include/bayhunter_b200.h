@@ -126,6 +126,10 @@ int bh_engine_synth_stride(const bh_engine* e);
  *                                        items (the rest take Love; 0 = no partition, the default)
  *   key "swd_split_waves"        0/1     Rayleigh and Love curves in one launch (default) or two
  *   key "swd_max_spec"           1..32   speculative bracket candidates per search
+ *   key "rf_prune_exp10"         0..300  receiver function: spectral bins whose Gauss-filter weight
+ *                                        exp(-(w/2a)^2) is below 10^-value are not computed (they enter the
+ *                                        inverse transform as 0); default 30, i.e. 1e-30 of the passband --
+ *                                        far below fp64 resolution of the trace; 0 computes every bin
  *   key "concurrent"             0/1     run SWD and RF kernels on forked streams
  *   key "profile"                0/1     record per-kernel event timings */
 int bh_engine_set(bh_engine* e, const char* key, int value);

@@ -455,3 +455,43 @@ def test_adaptive_record_capacity_never_changes_results():
         assert np.array_equal(got[2], want[2])
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[3], want[3], equal_nan=True)
     assert want_dp[2].mean() > 0.5 and (n_dp > 7).sum() > B // 2
+
+
+def test_rf_spectral_pruning_is_below_fp64_resolution(oracle):
+    """The spectrum kernel skips frequency bins whose Gauss-filter weight is < 1e-30 (default).  The
+    traces must equal the all-bins computation to ~1e-25 of the peak (they differ by terms that are
+    < 1e-30 of the passband), and both must match the oracle within the RF tolerance."""
+    from bayhunter_b200 import Engine, TargetSpec, synthetic
+    x = synthetic.rf_time_axis(dict(n=512, dt=0.1, t0=-5.0))
+    B = 64
+    rows, nlay = synthetic.draw_batch(B, (2, 12), seed=5)
+    for gauss in (0.8, 1.0, 2.5):
+        spec = [TargetSpec("prf", x, np.zeros(x.size), cov="exp", gauss=gauss)]
+        noise = synthetic.draw_noise(B, ["prf"], seed=6)
+        eng = Engine(spec, B, rows.shape[1])
+        eng.set(rf_prune_exp10=0)
+        full = eng.eval_host(rows, nlay, noise, want_synth=True)[3]
+        eng.set(rf_prune_exp10=30)
+        pruned = eng.eval_host(rows, nlay, noise, want_synth=True)[3]
+        peak = np.abs(full).max(axis=1, keepdims=True)
+        assert (np.abs(pruned - full) / peak).max() <= 1e-24, gauss
+        h, vp, vs, rho = synthetic.unpack(rows[3], int(nlay[3]))
+        _, yo = oracle.recfunc(h, vp, vs, rho, x, gauss=gauss)
+        assert np.abs(pruned[3] - yo).max() / np.abs(yo).max() <= 1e-9
+
+
+def test_rf_plugin_per_layer_q(oracle):
+    """qp / qs given per layer (rfmini_modrf.py:119-120 kwargs): the general complex-velocity path;
+    equal Q in every layer takes the hoisted one.  Both against the oracle."""
+    from bayhunter_b200 import RFminiModRF, synthetic
+    rng = np.random.default_rng(8)
+    x = -5.0 + 0.2 * np.arange(201)
+    for it in range(6):
+        k = int(rng.integers(2, 9))
+        h, vs = synthetic.draw_model(rng, k)
+        vp = vs * 1.75
+        rho = vp * 0.32 + 0.77
+        for qp, qs in ((rng.uniform(100, 900, k), rng.uniform(50, 400, k)), (np.full(k, 300.0), np.full(k, 120.0))):
+            t, y = RFminiModRF(x, "prf").run_model(h, vp, vs, rho, qp=qp, qs=qs)
+            _, yo = oracle.recfunc(h, vp, vs, rho, x, qp=qp, qs=qs)
+            assert np.abs(y - yo).max() / np.abs(yo).max() <= 1e-9, (it, qp[0])
