@@ -102,6 +102,12 @@ struct bh_engine {
   int sort_layers = 1;        // deal models to dispersion warps in that order
   int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
   int rf_first = 0;           // enqueue the RF kernels before the dispersion kernels
+  // The RF stream is released once this share of the dispersion warps has retired (0: no gate).  The
+  // evaluation is bound by the SUM of fp64 work, but the RF kernels must not get onto the SMs BEFORE
+  // the dispersion warps (which stream wins that race depends on what ran before): they would hold the
+  // registers the latency-critical searches need.
+  int rf_gate_pct = 25;
+  int* swd_done = nullptr;    // retired dispersion warps of the current evaluation
   // Spectral bins whose Gauss-filter weight exp(-(w/2a)^2) is below this are not computed: next to a
   // trace peak of order 0.1-1 they are below the resolution of fp64 (1e-30 vs 2e-16).  0 = all bins.
   double rf_floor = 1e-30;
@@ -290,6 +296,7 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
   if (rc == BH_OK) rc = scratch(e, &e->swd_queue, 2 + 1024);
   if (rc == BH_OK) rc = scratch(e, &e->swd_perm, B);
   if (rc == BH_OK) rc = scratch(e, &e->d_maxn, 1);
+  if (rc == BH_OK) rc = scratch(e, &e->swd_done, 1);
   if (rc == BH_OK && (cudaMallocHost((void**)&e->h_maxn, sizeof(int)) != cudaSuccess ||
                       cudaEventCreateWithFlags(&e->ev_maxn, cudaEventDisableTiming) != cudaSuccess))
     rc = set_err(BH_ERR_CUDA, "pinned readback buffer");
@@ -350,6 +357,9 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
     // bins with a Gauss weight below 10^-value are skipped; 0 disables the pruning
     if (value < 0 || value > 300) return set_err(BH_ERR_ARG, "rf_prune_exp10 must be 0 (off) or 1..300");
     e->rf_floor = value ? pow(10.0, -(double)value) : 0.0;
+  } else if (!strcmp(key, "rf_gate_pct")) {
+    if (value < 0 || value > 100) return set_err(BH_ERR_ARG, "rf_gate_pct must be 0..100");
+    e->rf_gate_pct = value;
   } else if (!strcmp(key, "rf_first")) {
     e->rf_first = value ? 1 : 0;
   } else if (!strcmp(key, "rf_after_love")) {
@@ -442,6 +452,8 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   PrepOut prep = e->prep;
   prep.swd_stride = odd_stride(lmax);   // rows of this batch; buffer is sized for max_layers
   BH_CUDA(cudaMemsetAsync(e->counters, 0, BH_NUM_COUNTERS * sizeof(unsigned long long), st));
+  const bool gated = e->rf_gate_pct > 0 && have_rf && nswd > 0 && e->concurrent && !e->rf_first;
+  if (gated) BH_CUDA(cudaMemsetAsync(e->swd_done, 0, sizeof(int), st));
 
   cudaStream_t st_rf = st;
   if (have_rf && nswd > 0 && e->concurrent) {
@@ -477,6 +489,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   };
   if (e->rf_first) launch_rf(st_rf);
   bool love_forked = false;
+  int gate_warps = 0;
   if (nswd > 0 || gen.ncurves > 0) {
     // record capacity of the main dispersion launch: the layer counts seen lately (+2), not lmax
     int cap = lmax;
@@ -571,6 +584,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       sw.curves = e->curves; sw.roots = e->roots; sw.curve_stride = e->curve_stride;
       sw.tstatus = e->tstatus; sw.counters = e->counters;
       sw.max_spec = e->max_spec;
+      sw.done = gated ? e->swd_done : nullptr;
       cudaStream_t sst = st;
       if (w == 1 && love_forked) sst = e->s_aux2;
       bool mixed = false;
@@ -603,6 +617,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
           sw.type_quota[1] = (int)((wl + (e->nsm - split) - 1) / (e->nsm - split));
           BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
         }
+        gate_warps += swd_warp_count(sw);
         if (pass == 0) { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
         else launch_swd(sw, sst);
       }
@@ -624,6 +639,8 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     }
   }
   if (love_forked && e->rf_after_love && st_rf != st) st_rf = e->s_aux2;
+  if (gated && st_rf != st && gate_warps > 0)
+    launch_swd_gate(e->swd_done, (int)((long long)gate_warps * e->rf_gate_pct / 100), st_rf);
   if (!e->rf_first) launch_rf(st_rf);
   if (st_rf != st && st_rf != e->s_aux2) {
     BH_CUDA(cudaEventRecord(e->ev_join, st_rf));

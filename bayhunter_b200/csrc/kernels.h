@@ -107,8 +107,11 @@ struct SwdLaunch {
   int type_quota[2];            // CTAs per SM that take the SM's own type before preferring the other
   int type_begin[3];            // filled by launch_swd: first warp of Rayleigh items, Love items, end
   int direct;                   // 1: no speculation (swd_kernel<true>), needs spw = 32 / 16
+  int* done;                    // += 1 per retired warp (null: not counted)
 };
 void launch_swd(SwdLaunch& p, cudaStream_t st);
+void launch_swd_gate(const int* done, int threshold, cudaStream_t st);
+int swd_warp_count(const SwdLaunch& p);
 size_t swd_smem_bytes(int lcap, int S);
 
 // Non-default SURF96 branches (higher modes, earth flattening, water layer): one thread

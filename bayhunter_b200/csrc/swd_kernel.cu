@@ -136,7 +136,10 @@ swd_kernel(SwdLaunch p) {
     const int n = p.nlay[BH_MODEL(sidx)];
     owner = n > p.nlay_lo && n <= p.nlay_hi;
   }
-  if (!__any_sync(0xffffffffu, owner)) return;
+  if (!__any_sync(0xffffffffu, owner)) {
+    if (lane == 0 && p.done) atomicAdd(p.done, 1);
+    return;
+  }
   Search s;
   SearchCtx ctx;
   ctx.omA = ws->omA; ctx.omB = ws->omB;
@@ -282,6 +285,7 @@ swd_kernel(SwdLaunch p) {
     evaluated += __shfl_down_sync(0xffffffffu, evaluated, d);
     consumed += __shfl_down_sync(0xffffffffu, consumed, d);
   }
+  if (lane == 0 && p.done) atomicAdd(p.done, 1);       // retired warps: releases the RF stream's gate (engine.cu)
   if (lane == 0 && p.counters) {
     atomicAdd(&p.counters[0], consumed);
     atomicAdd(&p.counters[1], evaluated);
@@ -291,6 +295,30 @@ swd_kernel(SwdLaunch p) {
 }
 
 }  // namespace
+
+// One thread that waits until `threshold` dispersion warps have retired (bounded: max_ns), so that
+// the work queued behind it in its stream starts in the dispersion kernel's tail whatever the order
+// in which the two streams happened to reach the device.
+__global__ void swd_gate_kernel(const int* done, int threshold, long long max_ns) {
+  long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    if (*(volatile const int*)done >= threshold) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > max_ns) break;
+    __nanosleep(2000);
+  }
+}
+
+void launch_swd_gate(const int* done, int threshold, cudaStream_t st) {
+  swd_gate_kernel<<<1, 1, 0, st>>>(done, threshold, 100LL * 1000 * 1000);
+}
+
+int swd_warp_count(const SwdLaunch& p) {
+  int warps = 0;
+  for (int c = 0; c < p.ncurves; ++c) warps += (p.B + p.spw[c] - 1) / p.spw[c];
+  return warps;
+}
 
 size_t swd_smem_bytes(int lcap, int S) {
   return (size_t)SWD_REC_FIELDS * lcap * S * sizeof(double) + sizeof(WarpShared);

@@ -288,6 +288,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     eng.set(profile=1)
+    if os.environ.get("BH_GATE"):        # developer sweep of the RF gate (tools/gpu_try.sh)
+        eng.set(rf_gate_pct=int(os.environ["BH_GATE"]))
     sampler = ClockSampler(local_rank)
     kernel_ms = {}
     counts = [0, 0]

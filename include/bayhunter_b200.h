@@ -130,6 +130,8 @@ int bh_engine_synth_stride(const bh_engine* e);
  *                                        exp(-(w/2a)^2) is below 10^-value are not computed (they enter the
  *                                        inverse transform as 0); default 30, i.e. 1e-30 of the passband --
  *                                        far below fp64 resolution of the trace; 0 computes every bin
+ *   key "rf_gate_pct"            0..100  the forked RF stream starts once this share of the dispersion
+ *                                        warps has retired (default 25; 0: no gate, the streams race)
  *   key "concurrent"             0/1     run SWD and RF kernels on forked streams
  *   key "profile"                0/1     record per-kernel event timings */
 int bh_engine_set(bh_engine* e, const char* key, int value);
