@@ -436,7 +436,9 @@ def main():
                        "valid_fraction": valid_frac, "parallelism": "chains sharded, dp%d" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "bh_engine_eval_host (pinned host buffers)", "matches_device_path": same},
-            "gpu_launches": (6 if c["rf"] is not None else 3) * K,
+            # per step: prepare(SWD rows), layer_order, swd_kernel, loglik (+ swd_gate, prepare(RF tables),
+            # rf_spectrum, rf_synth with an RF target)
+            "gpu_launches": (8 if c["rf"] is not None else 4) * K,
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": dom_bytes / dom_s / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": dom_bytes,
