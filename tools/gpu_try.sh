@@ -1,10 +1,13 @@
 #!/bin/bash
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for g in 0 10 25 40 60; do
-BH_GATE=$g python bench.py --steps 30 --warmup 3 --no-cpu-baseline --sampler-iters 0 2>&1 | python -c "
+for v in default sm128 sm64 sm128mb5 rfmb5 rfmb6; do
+  if [ "$v" = default ]; then unset BH_B200_LIB; else export BH_B200_LIB=$PWD/bayhunter_b200/variants/libbh_$v.so; fi
+  python tools/quick_bench.py joint5 8192 concurrent=1 concurrent=0 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('gate', '$g', 'ms_per_step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), {k:round(v,2) for k,v in d['kernel_ms'].items()})
+    if not l.startswith('{'): continue
+    d=json.loads(l); print('$v', 'conc', d['concurrent'], 'total', d['total_ms'], {k:round(v,3) for k,v in d['kernels'].items() if k.startswith('rf') or k=='swd'})
 "
 done
+unset BH_B200_LIB
+python tools/quick_bench.py transd3 4096 concurrent=1 concurrent=0 2>&1 | python tools/fmt_ab.py | grep -v lib | cut -c1-250
