@@ -1,0 +1,54 @@
+"""tools/make_profiles.py <tag> [round]: copy the judged summaries of a tools/gpu_record.sh run from
+gpurun_out/ (scratch) into profiles/ (tracked): bench lines, ncu launch list + per-kernel shares,
+ncu --set full summaries of the dispersion and RF spectrum kernels, DRAM traffic per launch."""
+import collections, csv, io, json, os, shutil, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]; rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+shutil.copy(os.path.join(G, tag + "_bench.json"), os.path.join(P, rnd + "_bench.json"))
+shutil.copy(os.path.join(G, tag + "_bench_ref.json"), os.path.join(P, rnd + "_bench_reference_arm.json"))
+shutil.copy(os.path.join(G, tag + "_launches.csv"), os.path.join(P, rnd + "_launches.csv"))
+
+rows = [r for r in csv.reader(open(os.path.join(G, tag + "_launches.csv"))) if len(r) > 5]
+hdr = None; agg = collections.OrderedDict()
+for r in rows:
+    if r[0] == "ID": hdr = r; continue
+    if hdr is None: continue
+    d = dict(zip(hdr, r))
+    try: v = float(d["Metric Value"].replace(",", ""))
+    except ValueError: continue
+    u = d["Metric Unit"]
+    ms = v / 1e6 if u.startswith("n") else (v / 1e3 if u.startswith("u") else v)
+    name = d["Kernel Name"].split("(")[0].split("::")[-1]
+    a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += ms
+tot = sum(a[1] for a in agg.values())
+with open(os.path.join(P, rnd + "_launch_shares.txt"), "w") as f:
+    f.write("# per-kernel totals of profiles/%s_launches.csv (ncu --metrics gpu__time_duration.sum --clock-control none;\n"
+            "# python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sampler-iters 2: 5 evaluations + the e2e pass + a short sampler run).\n"
+            "# Times under ncu are cold-cache and serialised: the SHARES are what carries over to the live step.\n" % rnd)
+    f.write("%-44s %8s %10s %7s\n" % ("kernel", "launches", "total ms", "share"))
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write("%-44s %8d %10.3f %6.1f%%\n" % (k[:44], n, t, 100 * t / tot))
+
+traffic = {}
+for kern, short in (("swd", "swd_kernel"), ("rf", "rf_spectrum")):
+    rep = os.path.join(G, "%s_%s.ncu-rep" % (tag, kern))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_kernels.py"), rep], capture_output=True, text=True).stdout
+    hist = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    hist = hist[hist.index("warp instructions executed"):] if "warp instructions executed" in hist else ""
+    with open(os.path.join(P, "%s_%s_ncu_summary.txt" % (rnd, short if kern == "rf" else "swd_kernel")), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s -s 3 -c 1 python bench.py --steps 1 --warmup 3 "
+                "--no-cpu-baseline --sampler-iters 0  (joint5, B = 8192, one launch after 3 warm-up steps)\n" % short)
+        f.write(out)
+        f.write("\n## SASS opcode histogram (executed warp instructions)\n" + hist)
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw))); h = rr[0]; units = rr[1]; vals = rr[2]
+    tb = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = h.index(key); v = float(vals[i].replace(",", "")); u = units[i].lower()
+        tb += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+    traffic[short + ("_kernel" if kern == "rf" else "")] = int(tb)
+tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in this directory (bytes)",
+      "joint5": {"swd_kernel": traffic["swd_kernel"], "rf_spectrum_kernel": traffic["rf_spectrum_kernel"]}}
+json.dump(tj, open(os.path.join(P, "traffic.json"), "w"), indent=2)
+print(open(os.path.join(P, rnd + "_launch_shares.txt")).read()); print(tj)
