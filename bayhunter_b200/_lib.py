@@ -65,6 +65,7 @@ SIGNATURES = {
     "bh_abi_version": (ctypes.c_int, []),
     "bh_last_error": (ctypes.c_char_p, []),
     "bh_device_count": (ctypes.c_int, []),
+    "bh_set_device": (ctypes.c_int, [ctypes.c_int]),
     "bh_engine_create": (ctypes.c_int, [ctypes.POINTER(BhTarget), ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "bh_engine_destroy": (None, [ctypes.c_void_p]),
@@ -130,6 +131,11 @@ def check(code):
         msg = load().bh_last_error()
         raise BayHunterB200Error(code, msg.decode() if msg else "")
     return code
+
+
+def set_device(index):
+    """Select the GPU of this process (torchrun: LOCAL_RANK) for engines / samplers created later."""
+    check(require_device().bh_set_device(int(index)))
 
 
 def require_device():

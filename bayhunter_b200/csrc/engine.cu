@@ -174,6 +174,12 @@ int bh_device_count(void) {
   return n;
 }
 
+int bh_set_device(int device) {
+  if (bh_device_count() < 1) return set_err(BH_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+  BH_CUDA(cudaSetDevice(device));
+  return BH_OK;
+}
+
 void bh_engine_destroy(bh_engine* e) {
   if (!e) return;
   for (void* p : e->owned) cudaFree(p);

@@ -51,6 +51,9 @@ class MCMC_Optimizer(object):
         self.initparams = dict(_sc.DEFAULT_INITPARAMS); self.initparams.update(initparams)
         self.station = self.initparams.get('station')
         self.targets = targets
+        if "LOCAL_RANK" in os.environ:                 # one process per GPU
+            from . import _lib
+            _lib.set_device(int(os.environ["LOCAL_RANK"]))
         self.rank = int(os.environ.get("RANK", 0)) if rank is None else int(rank)
         self.world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else int(world_size)
 

@@ -255,6 +255,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     bh._lib.require_device()
+    bh._lib.set_device(local_rank)
 
     cfg = args.config
     B = args.chains_per_gpu or synthetic.CONFIGS[cfg]["B"]

@@ -93,6 +93,9 @@ typedef struct bh_engine bh_engine;
 int bh_abi_version(void);
 const char* bh_last_error(void);
 int bh_device_count(void);
+/* Device of the calling thread for everything this library creates afterwards (one process per GPU:
+ * pass LOCAL_RANK).  Without it the library adopts the thread's current CUDA context, else device 0. */
+int bh_set_device(int device);
 
 /*
  * Create an engine for a fixed joint target set.  Uploads observed data,

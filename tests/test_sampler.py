@@ -241,3 +241,19 @@ def test_synthobs_noise_matches_reference(golden_dir):
         y = np.zeros(n)
         assert np.array_equal(so_mod.compute_expnoise(y, corr=0.6, sigma=0.02), fx["exp_%d" % n])
         assert np.array_equal(so_mod.compute_gaussnoise(y, corr=0.9, sigma=0.005), fx["gauss_%d" % n])
+
+
+def test_load_params_reads_the_reference_ini_dialect(tmp_path):
+    """utils.load_params on an .ini with the keys of BayHunter's tutorial/config.ini (values evaluated
+    like src/utils.py:44-70: expressions, None, comma lists; station / savepath stay strings)."""
+    from bayhunter_b200 import utils
+    ini = tmp_path / "config.ini"
+    ini.write_text("[modelpriors]\nvpvs = 1.4, 2.1\nlayers = 1, 20\nmohoest = None\nrfnoise_corr = 0.9\n"
+                   "swdnoise_corr = 0.\nrfnoise_sigma = 1e-5, 0.05   # comment\n\n[initparams]\nnchains = 5\n"
+                   "iter_burnin = (2048 * 16)\npropdist = 0.015, 0.015, 0.015, 0.005, 0.005\nacceptance = 40, 45\n"
+                   "lvz = None\nrcond= 1e-5\nstation = 'test'\nsavepath = 'results'\n[datapaths]\nx = y\n")
+    priors, ip = utils.load_params(str(ini))
+    assert priors == dict(vpvs=[1.4, 2.1], layers=[1, 20], mohoest=None, rfnoise_corr=0.9, swdnoise_corr=0.0,
+                          rfnoise_sigma=[1e-5, 0.05])
+    assert ip == dict(nchains=5, iter_burnin=32768, propdist=[0.015, 0.015, 0.015, 0.005, 0.005], acceptance=[40, 45],
+                      lvz=None, rcond=1e-5, station='test', savepath='results')
