@@ -100,8 +100,6 @@ struct bh_engine {
   int autotune = 0;
   cudaEvent_t ev_tune[2] = {nullptr, nullptr};
   int sort_layers = 1;        // deal models to dispersion warps in that order
-  int rf_after_love = 0;      // with split waves: RF kernels queue behind the (short) Love launch
-  int rf_first = 0;           // enqueue the RF kernels before the dispersion kernels
   // The RF stream is released once this share of the dispersion warps has retired (0: no gate).  The
   // evaluation is bound by the SUM of fp64 work, but the RF kernels must not get onto the SMs BEFORE
   // the dispersion warps (which stream wins that race depends on what ran before): they would hold the
@@ -366,10 +364,6 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "rf_gate_pct")) {
     if (value < 0 || value > 100) return set_err(BH_ERR_ARG, "rf_gate_pct must be 0..100");
     e->rf_gate_pct = value;
-  } else if (!strcmp(key, "rf_first")) {
-    e->rf_first = value ? 1 : 0;
-  } else if (!strcmp(key, "rf_after_love")) {
-    e->rf_after_love = value ? 1 : 0;
   } else if (!strcmp(key, "swd_autotune")) {
     e->autotune = value ? 1 : 0;
     e->tune = bh_engine::Tune();
@@ -458,7 +452,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   PrepOut prep = e->prep;
   prep.swd_stride = odd_stride(lmax);   // rows of this batch; buffer is sized for max_layers
   BH_CUDA(cudaMemsetAsync(e->counters, 0, BH_NUM_COUNTERS * sizeof(unsigned long long), st));
-  const bool gated = e->rf_gate_pct > 0 && have_rf && nswd > 0 && e->concurrent && !e->rf_first;
+  const bool gated = e->rf_gate_pct > 0 && have_rf && nswd > 0 && e->concurrent;
   if (gated) BH_CUDA(cudaMemsetAsync(e->swd_done, 0, sizeof(int), st));
 
   cudaStream_t st_rf = st;
@@ -469,7 +463,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   }
 
   for (bool& u : e->pev_used) u = false;
-  // receiver-function launches of this evaluation (enqueued before or after the dispersion launches)
+  // receiver-function launches of this evaluation
   auto launch_rf = [&](cudaStream_t st_rf) {
   for (int t = 0; t < ts.ntargets; ++t) {
     const TargetDev& d = ts.t[t];
@@ -493,7 +487,6 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     { KTimer kt(e, BH_K_RF_SYNTH, st_rf); launch_rf_synth(rf, st_rf); }
   }
   };
-  if (e->rf_first) launch_rf(st_rf);
   bool love_forked = false;
   int gate_warps = 0;
   if (nswd > 0 || gen.ncurves > 0) {
@@ -644,11 +637,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       e->maxn_pending = true;
     }
   }
-  if (love_forked && e->rf_after_love && st_rf != st) st_rf = e->s_aux2;
   if (gated && st_rf != st && gate_warps > 0)
     launch_swd_gate(e->swd_done, (int)((long long)gate_warps * e->rf_gate_pct / 100), st_rf);
-  if (!e->rf_first) launch_rf(st_rf);
-  if (st_rf != st && st_rf != e->s_aux2) {
+  launch_rf(st_rf);
+  if (st_rf != st) {
     BH_CUDA(cudaEventRecord(e->ev_join, st_rf));
     BH_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
   }
