@@ -337,6 +337,8 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
 
 int bh_engine_synth_stride(const bh_engine* e) { return e ? e->ts.synth_stride : BH_ERR_ARG; }
 
+int bh_engine_is_tuning(const bh_engine* e) { return (e && e->autotune && e->tune.locked < 0) ? 1 : 0; }
+
 int bh_engine_set(bh_engine* e, const char* key, int value) {
   if (!e || !key) return set_err(BH_ERR_ARG, "null engine/key");
   if (!strcmp(key, "swd_searches_per_warp")) {
@@ -556,7 +558,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
               t.cur = next;
             }
           }
-          if (t.locked < 0) { pick = t.cand[t.cur]; tuning_now = !t.pending; }
+          if (t.locked < 0 && !t.pending) {            // time ONE evaluation with the candidate under test;
+            pick = t.cand[t.cur];                      // while that measurement is in flight (the host may be
+            tuning_now = true;                         // far ahead of the device) keep the rule's pick
+          }
         }
         if (t.locked >= 0) pick = t.locked;
       }

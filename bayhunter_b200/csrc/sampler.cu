@@ -357,6 +357,9 @@ int bh_sampler_run(bh_sampler* s, int niter) {
                             s->p_misfits, s->p_status, nullptr, s->st);
     if (rc != BH_OK) return rc;
     sampler_accept_kernel<<<blocks, threads, 0, s->st>>>(p);
+    // while the engine is still timing its models-per-warp candidates (the first ~10 iterations of a
+    // batch size) let each iteration finish, so that its timing is read before the next one is enqueued
+    if (bh_engine_is_tuning(s->eng)) SMP_CUDA(cudaStreamSynchronize(s->st));
   }
   SMP_CUDA(cudaGetLastError());
   SMP_CUDA(cudaStreamSynchronize(s->st));

@@ -109,6 +109,11 @@ void bh_engine_destroy(bh_engine* e);
 /* Size of one model's synthetic-data row: sum of n over targets. */
 int bh_engine_synth_stride(const bh_engine* e);
 
+/* 1 while "swd_autotune" is still timing candidates for the current batch size (a caller that enqueues
+ * evaluations without ever waiting can synchronise its stream between them until this returns 0, so
+ * that every timing is read back before the next candidate is tried). */
+int bh_engine_is_tuning(const bh_engine* e);
+
 /* Tunables (call before eval; all have working defaults).
  *   key "swd_searches_per_warp"  1..32   phase-velocity curves (default chosen from the batch size)
  *   key "swd_group_searches_per_warp" 1..32  group-velocity curves (default: half of the above)
