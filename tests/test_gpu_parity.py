@@ -495,3 +495,36 @@ def test_rf_plugin_per_layer_q(oracle):
             t, y = RFminiModRF(x, "prf").run_model(h, vp, vs, rho, qp=qp, qs=qs)
             _, yo = oracle.recfunc(h, vp, vs, rho, x, qp=qp, qs=qs)
             assert np.abs(y - yo).max() / np.abs(yo).max() <= 1e-9, (it, qp[0])
+
+
+def test_maximum_sizes_and_empty_batch(oracle):
+    """SURF96's array limits (NL = 100 rows, NP = 60 periods, surfdisp96.f:60-62) through the batched
+    engine, and an empty batch."""
+    from bayhunter_b200 import Engine, TargetSpec, synthetic
+    from oracle import joint_oracle as jo
+    rng = np.random.default_rng(17)
+    periods = np.linspace(1, 60, 60)
+    x_rf = synthetic.rf_time_axis(dict(n=201, dt=0.2, t0=-5.0))
+    specs = [TargetSpec("rdispph", periods, 3.5 + rng.normal(0, .1, 60), cov="exp"),
+             TargetSpec("ldispgr", periods, 3.5 + rng.normal(0, .1, 60), cov="exp"),
+             TargetSpec("prf", x_rf, rng.normal(0, .02, x_rf.size), cov="exp")]
+    ot = [jo.OracleTarget(s.ref, s.x, s.y, cov="exp") for s in specs]
+    B = 6
+    rows = np.zeros((B, 100, 4)); nlay = np.zeros(B, dtype=np.int32)
+    for b, k in enumerate((100, 100, 97, 64, 2, 100)):
+        vs = np.sort(rng.uniform(2.0, 4.8, k)); h = np.concatenate((rng.uniform(0.3, 0.9, k - 1), [0.0]))
+        vpvs = rng.uniform(1.6, 1.9)
+        rows[b, :k, 0] = vs; rows[b, :k, 1] = vpvs; rows[b, :k, 3] = h
+        rows[b, 1:k, 2] = np.cumsum(h)[:-1]
+        nlay[b] = k
+    noise = synthetic.draw_noise(B, [s.ref for s in specs], seed=9)
+    eng = Engine(specs, B, 100)
+    out = eng.eval_host(rows, nlay, noise, want_synth=True)
+    ref = oracle.evaluate_batch(ot, rows, nlay, noise)
+    _compare(out, ref, [(s.ref, s.n) for s in specs])
+    assert ref[2].sum() >= 5
+    e = _logl_check(out[0], ref[0], ref[2] == 1)
+    assert np.median(e) <= 1e-6
+    # B = 0: nothing to do, no error
+    empty = eng.eval_host(rows[:0], nlay[:0], noise[:0])
+    assert empty[0].size == 0 and empty[2].size == 0
