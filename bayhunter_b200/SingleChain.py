@@ -67,7 +67,7 @@ def set_target_covariance(targets, priors, rcond=None):
             target.get_covariance = target.valuation.get_covariance_exp
 
 
-def make_config(targets, priors, initparams, seed=0, max_accepted=None, nchains=None):
+def make_config(targets, priors, initparams, seed=0, max_accepted=None, nchains=None, max_chain_bytes=32 << 30):
     """BayHunter dictionaries -> struct bh_sampler_config."""
     c = _lib.BhSamplerConfig()
     c.layers_min, c.layers_max = int(priors['layers'][0]), int(priors['layers'][1])
@@ -99,13 +99,16 @@ def make_config(targets, priors, initparams, seed=0, max_accepted=None, nchains=
         # The reference sizes its chain arrays as iterations * max(acceptance) / 100
         # (mcmcOptimizer.py:86-88) and dies with an IndexError when a chain accepts more.  Device
         # memory is cheap: keep one row per iteration while the arrays stay below ~4 GB, else the
-        # reference's size plus a quarter.
+        # reference's size plus a quarter -- but never more than `max_chain_bytes` (32 GB of the B200's
+        # 180 GB) for the whole ensemble: beyond that accepted models are counted as overflow, not stored.
         iterations = c.iter_burnin + c.iter_main
         row_bytes = 4 * (2 * (c.layers_max + 1) + 3 * targets.ntargets + 4)
-        if nchains is not None and (iterations + 1) * row_bytes * int(nchains) <= (4 << 30):
+        n = int(nchains) if nchains is not None else int(initparams.get('nchains', 1))
+        if (iterations + 1) * row_bytes * n <= (4 << 30):
             max_accepted = iterations + 1
         else:
             max_accepted = int(1.25 * iterations * np.max(initparams['acceptance']) / 100.) + 16
+            max_accepted = min(max_accepted, max(64, int(max_chain_bytes // (row_bytes * n))))
     c.max_accepted = max(int(max_accepted), 1)
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return c

@@ -186,6 +186,9 @@ def test_initial_draws_follow_reference_sequence():
     c = sc.make_config(jt, priors, ip, seed=5)
     assert c.noise_fixed[0] == 1 and c.noise_fixed[1] == 0 and c.max_accepted == int(1.25 * 6144 * 45 / 100.) + 16
     assert sc.make_config(jt, priors, ip, seed=5, nchains=8).max_accepted == 6145
+    big = dict(ip); big.update(iter_burnin=100000, iter_main=50000)
+    cb = sc.make_config(jt, priors, big, seed=5, nchains=65536)
+    assert cb.max_accepted * 65536 * 4 * (2 * 11 + 3 * 2 + 4) <= (32 << 30) and cb.max_accepted >= 64
     assert (c.layers_min, c.layers_max, c.vpvs_fixed, c.has_mantle) == (2, 10, 0, 0)
 
 
