@@ -184,7 +184,7 @@ def test_initial_draws_follow_reference_sequence():
     sc.set_target_covariance(jt, priors, None)
     assert [tt.covariance_law() for tt in jt.targets] == ["white", "exp"]
     c = sc.make_config(jt, priors, ip, seed=5)
-    assert c.noise_fixed[0] == 1 and c.noise_fixed[1] == 0 and c.max_accepted == int(1.25 * 6144 * 45 / 100.) + 16
+    assert c.noise_fixed[0] == 1 and c.noise_fixed[1] == 0 and c.max_accepted == 6145     # one row per iteration fits
     assert sc.make_config(jt, priors, ip, seed=5, nchains=8).max_accepted == 6145
     big = dict(ip); big.update(iter_burnin=100000, iter_main=50000)
     cb = sc.make_config(jt, priors, big, seed=5, nchains=65536)
