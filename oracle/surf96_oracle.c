@@ -12,8 +12,11 @@
  * cannot be compiled into oracle/_ref.  Parity is pinned to the four
  * golden dispersion fixtures of the reference (tutorial/observed/
  * st3_{r,l}disp{ph,gr}.dat, 4 decimals => +-5e-5 km/s); beyond that
- * precision parity is UNPINNED by any reference artefact (stated in
- * DESIGN.md).
+ * precision no reference ARTEFACT pins it (stated in DESIGN.md), but
+ * oracle/first_principles.py does: the phase velocities returned here
+ * (fundamental and first higher mode) are zeros of the exact layered-
+ * medium eigenproblem within 1.2e-6 c, the reference's own search
+ * tolerance (tests/test_oracle.py).
  *
  * Typing follows the Fortran exactly (the file has no IMPLICIT NONE in
  * the main routine): model arrays, start value, group-velocity formula
