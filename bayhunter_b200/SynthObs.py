@@ -19,85 +19,73 @@ logger = logging.getLogger()
 rstate = np.random.RandomState(333)
 
 
+def _forward(classes, x, h, vs, vpvs, **plugin_params):
+    """ref -> array([x, y]) for each target class, from one layered model (rho by Berteussen)."""
+    h, vs = np.array(h), np.array(vs)
+    vp = vs * vpvs
+    rho = vp * 0.32 + 0.77
+    out = {}
+    for cls in classes:
+        target = cls(x=x, y=None)
+        target.moddata.plugin.set_modelparams(**plugin_params)
+        out[target.ref] = np.array(target.moddata.plugin.run_model(h=h, vp=vp, vs=vs, rho=rho))
+    return out
+
+
+def _correlated_noise(n, rmatrix, sigma):
+    return rstate.multivariate_normal(np.zeros(n), sigma ** 2 * rmatrix)
+
+
+def _lag_matrix(n):
+    i = np.arange(n)
+    return np.abs(i[:, None] - i[None, :]).astype(float)
+
+
 class SynthObs():
     @staticmethod
     def return_swddata(h, vs, vpvs=1.73, pars=dict(), x=None):
-        """Dictionary ref -> [x, y] of the four dispersion curves (src/SynthObs.py:25-58)."""
-        if x is None:
-            x = np.linspace(1, 40, 20)
-        h = np.array(h)
-        vs = np.array(vs)
-        mode = pars.get('mode', 1)
-        vp = vs * vpvs
-        rho = vp * 0.32 + 0.77
-        data = {}
-        for cls in (Targets.RayleighDispersionPhase, Targets.RayleighDispersionGroup,
-                    Targets.LoveDispersionPhase, Targets.LoveDispersionGroup):
-            target = cls(x=x, y=None)
-            target.moddata.plugin.set_modelparams(mode=mode)
-            xmod, ymod = target.moddata.plugin.run_model(h=h, vp=vp, vs=vs, rho=rho)
-            data[target.ref] = np.array([xmod, ymod])
+        """The four dispersion curves of a model (src/SynthObs.py:25-58); pars: {'mode': n}."""
+        x = np.linspace(1, 40, 20) if x is None else x
+        data = _forward((Targets.RayleighDispersionPhase, Targets.RayleighDispersionGroup,
+                         Targets.LoveDispersionPhase, Targets.LoveDispersionGroup), x, h, vs, vpvs,
+                        mode=pars.get('mode', 1))
         logger.info('Compute SWD for %d periods, with model vp/vs %.2f.' % (x.size, vpvs))
         return data
 
     @staticmethod
     def return_rfdata(h, vs, vpvs=1.73, pars=dict(), x=None):
-        """Dictionary ref -> [x, y] of the P and S receiver functions (src/SynthObs.py:60-101)."""
-        if x is None:
-            x = np.linspace(-5, 35, 201)
-        h = np.array(h)
-        vs = np.array(vs)
-        gauss = pars.get('gauss', 1.0)
-        water = pars.get('water', 0.001)
-        p = pars.get('p', 6.4)
-        nsv = pars.get('nsv', None)
-        vp = vs * vpvs
-        rho = vp * 0.32 + 0.77
-        data = {}
-        for cls in (Targets.PReceiverFunction, Targets.SReceiverFunction):
-            target = cls(x=x, y=None)
-            target.moddata.plugin.set_modelparams(gauss=gauss, water=water, p=p, nsv=nsv)
-            xmod, ymod = target.moddata.plugin.run_model(h=h, vp=vp, vs=vs, rho=rho)
-            data[target.ref] = np.array([xmod, ymod])
-        logger.info('Compute RF with gauss: %.2f, waterlevel: %.4f, slowness: %.2f' % (gauss, water, p))
+        """P and S receiver functions of a model (src/SynthObs.py:60-101); pars: gauss, water, p, nsv."""
+        x = np.linspace(-5, 35, 201) if x is None else x
+        kw = dict(gauss=pars.get('gauss', 1.0), water=pars.get('water', 0.001), p=pars.get('p', 6.4),
+                  nsv=pars.get('nsv', None))
+        data = _forward((Targets.PReceiverFunction, Targets.SReceiverFunction), x, h, vs, vpvs, **kw)
+        logger.info('Compute RF with gauss: %.2f, waterlevel: %.4f, slowness: %.2f' % (kw['gauss'], kw['water'], kw['p']))
         return data
 
     @staticmethod
     def save_data(data, outfile=None):
-        """ASCII files, one per reference (src/SynthObs.py:103-118)."""
-        if outfile is None:
-            outfile = 'syn_%s.dat'
+        """One two-column ASCII file per reference, 4 decimals (src/SynthObs.py:103-118)."""
+        outfile = 'syn_%s.dat' if outfile is None else outfile
         if '%s' not in outfile:
-            name, ext = os.path.splitext(outfile)
-            outfile = name + '_%s.' + ext
-        for ref in data.keys():
-            x, y = data[ref]
-            with open(outfile % ref, 'w') as f:
-                for i in range(len(x)):
-                    f.write('%.4f\t%.4f\n' % (x[i], y[i]))
+            stem, ext = os.path.splitext(outfile)
+            outfile = stem + '_%s.' + ext
+        for ref, (x, y) in data.items():
+            np.savetxt(outfile % ref, np.column_stack((x, y)), fmt='%.4f', delimiter='\t')
 
     @staticmethod
     def save_model(h, vs, vpvs=1.73, outfile=None):
-        """ASCII model table (src/SynthObs.py:120-135)."""
-        h = np.array(h)
+        """ASCII model table through the RF plugin's writer (src/SynthObs.py:120-135)."""
         vs = np.array(vs)
         vp = vs * vpvs
-        rho = vp * 0.32 + 0.77
-        if outfile is None:
-            outfile = 'syn_mod.dat'
-        target = Targets.PReceiverFunction(x=np.arange(10), y=None)
-        target.moddata.plugin.write_startmodel(h, vp, vs, rho, outfile)
+        writer = Targets.PReceiverFunction(x=np.arange(10), y=None).moddata.plugin
+        writer.write_startmodel(np.array(h), vp, vs, vp * 0.32 + 0.77, 'syn_mod.dat' if outfile is None else outfile)
 
     @staticmethod
     def compute_expnoise(data_obs, corr=0.85, sigma=0.0125):
-        """Exponentially correlated noise (src/SynthObs.py:137-145)."""
-        idx = np.fromfunction(lambda i, j: (abs((i + j) - 2 * i)), (data_obs.size, data_obs.size))
-        Ce = sigma ** 2 * corr ** idx
-        return rstate.multivariate_normal(np.zeros(data_obs.size), Ce)
+        """Exponentially correlated noise, R_ij = corr^|i-j| (src/SynthObs.py:137-145)."""
+        return _correlated_noise(data_obs.size, corr ** _lag_matrix(data_obs.size), sigma)
 
     @staticmethod
     def compute_gaussnoise(data_obs, corr=0.85, sigma=0.0125):
-        """Gaussian correlated noise (src/SynthObs.py:147-155)."""
-        idx = np.fromfunction(lambda i, j: (abs((i + j) - 2 * i)), (data_obs.size, data_obs.size))
-        Ce = sigma ** 2 * corr ** (idx ** 2)
-        return rstate.multivariate_normal(np.zeros(data_obs.size), Ce)
+        """Gaussian correlated noise, R_ij = corr^(|i-j|^2) (src/SynthObs.py:147-155)."""
+        return _correlated_noise(data_obs.size, corr ** (_lag_matrix(data_obs.size) ** 2), sigma)

@@ -43,21 +43,19 @@ class ModeledData(object):
     """Holds the forward-modelling plugin and the latest synthetic (x, y)."""
 
     def __init__(self, obsx, ref):
-        if ref in RF_REFS:
-            from .rfmini_modrf import RFminiModRF
-            self.plugin = RFminiModRF(obsx, ref)
-            self.xlabel = "Time in s"
-        elif ref in SWD_REFS:
-            from .surf96_modsw import SurfDisp
-            self.plugin = SurfDisp(obsx, ref)
-            self.xlabel = "Period in s"
+        self.x = self.y = np.nan
+        self.plugin, self.xlabel = None, "x"
+        kind = "rf" if ref in RF_REFS else "swd" if ref in SWD_REFS else None
+        if kind == "rf":
+            from .rfmini_modrf import RFminiModRF as plugin_cls
+        elif kind == "swd":
+            from .surf96_modsw import SurfDisp as plugin_cls
         else:
-            logger.info("Please provide a forward modeling plugin for your target.\n"
-                        "Use target.update_plugin(MyForwardClass())")
-            self.plugin = None
-            self.xlabel = "x"
-        self.x = np.nan
-        self.y = np.nan
+            logger.info("No forward plugin is known for ref %r: attach one with "
+                        "target.update_plugin(MyForwardClass())" % (ref,))
+            return
+        self.plugin = plugin_cls(obsx, ref)
+        self.xlabel = {"rf": "Time in s", "swd": "Period in s"}[kind]
 
     def update(self, plugin):
         self.plugin = plugin
@@ -148,28 +146,20 @@ class SingleTarget(object):
                              "equivalent" % (self.ref, name))
 
     def _moddata_valid(self):
-        if not type(self.moddata.x) == np.ndarray:
-            return False
-        if not len(self.obsdata.x) == len(self.moddata.x):
-            return False
-        if not np.sum(self.obsdata.x - self.moddata.x) <= 1e-5:
-            return False
-        if not len(self.obsdata.y) == len(self.moddata.y):
-            return False
-        return True
+        """The reference's acceptance test of a synthetic (src/Targets.py:204-214): an array of the
+        observed length whose abscissa agrees in the (signed!) sum to 1e-5."""
+        mx, my, ox = self.moddata.x, self.moddata.y, self.obsdata.x
+        return (type(mx) == np.ndarray and len(mx) == len(ox) and bool(np.sum(ox - mx) <= 1e-5)
+                and len(my) == len(self.obsdata.y))
 
     def calc_misfit(self):
-        if not self._moddata_valid():
-            self.valuation.misfit = 1e15
-            return
-        self.valuation.misfit = self.valuation.get_rms(self.obsdata.y, self.moddata.y)
+        ok = self._moddata_valid()
+        self.valuation.misfit = self.valuation.get_rms(self.obsdata.y, self.moddata.y) if ok else 1e15
 
     def calc_likelihood(self, c_inv, logc_det):
-        if not self._moddata_valid():
-            self.valuation.likelihood = -1e15
-            return
-        self.valuation.likelihood = self.valuation.get_likelihood(
-            self.obsdata.y, self.moddata.y, c_inv, logc_det)
+        ok = self._moddata_valid()
+        self.valuation.likelihood = (self.valuation.get_likelihood(self.obsdata.y, self.moddata.y, c_inv, logc_det)
+                                     if ok else -1e15)
 
     def to_spec(self):
         """Engine description of this target (observed data, law, plugin parameters)."""
@@ -190,46 +180,22 @@ class SingleTarget(object):
         return TargetSpec(self.ref, self.obsdata.x, y, cov=law, **kw, **params)
 
 
-class RayleighDispersionPhase(SingleTarget):
-    noiseref = "swd"
-
+def _target_class(name, ref, noiseref):
+    """Target class of BayHunter's name (src/Targets.py:252-297): fixes `ref` and the family of noise
+    priors (`swd` / `rf`) its hyper-parameters are drawn from."""
     def __init__(self, x, y, yerr=None):
-        SingleTarget.__init__(self, x, y, "rdispph", yerr=yerr)
+        SingleTarget.__init__(self, x, y, ref, yerr=yerr)
+    cls = type(name, (SingleTarget,), {"__init__": __init__, "noiseref": noiseref, "__module__": __name__,
+                                       "__doc__": "%s target (ref %r, noise priors %r)." % (name, ref, noiseref)})
+    return cls
 
 
-class RayleighDispersionGroup(SingleTarget):
-    noiseref = "swd"
-
-    def __init__(self, x, y, yerr=None):
-        SingleTarget.__init__(self, x, y, "rdispgr", yerr=yerr)
-
-
-class LoveDispersionPhase(SingleTarget):
-    noiseref = "swd"
-
-    def __init__(self, x, y, yerr=None):
-        SingleTarget.__init__(self, x, y, "ldispph", yerr=yerr)
-
-
-class LoveDispersionGroup(SingleTarget):
-    noiseref = "swd"
-
-    def __init__(self, x, y, yerr=None):
-        SingleTarget.__init__(self, x, y, "ldispgr", yerr=yerr)
-
-
-class PReceiverFunction(SingleTarget):
-    noiseref = "rf"
-
-    def __init__(self, x, y, yerr=None):
-        SingleTarget.__init__(self, x, y, "prf", yerr=yerr)
-
-
-class SReceiverFunction(SingleTarget):
-    noiseref = "rf"
-
-    def __init__(self, x, y, yerr=None):
-        SingleTarget.__init__(self, x, y, "srf", yerr=yerr)
+RayleighDispersionPhase = _target_class("RayleighDispersionPhase", "rdispph", "swd")
+RayleighDispersionGroup = _target_class("RayleighDispersionGroup", "rdispgr", "swd")
+LoveDispersionPhase = _target_class("LoveDispersionPhase", "ldispph", "swd")
+LoveDispersionGroup = _target_class("LoveDispersionGroup", "ldispgr", "swd")
+PReceiverFunction = _target_class("PReceiverFunction", "prf", "rf")
+SReceiverFunction = _target_class("SReceiverFunction", "srf", "rf")
 
 
 class JointTarget(object):
