@@ -190,3 +190,46 @@ def test_inversion_converges_and_writes_reference_files(tmp_path):
     vs_at = np.array(vs_at)
     med = np.median(vs_at, axis=0)
     assert abs(med[0] - 2.7) < 0.35 and abs(med[1] - 3.6) < 0.25 and abs(med[2] - 4.4) < 0.35, med
+
+
+def test_whole_chains_of_the_reference_are_reproduced(golden_dir):
+    """BASELINE config 1 (tutorial set-up: Rayleigh phase K = 21 + P-RF n = 201, 4 chains x 2048
+    iterations) as a golden vector: tests/golden/make_chain_fixture.py ran the REFERENCE's SingleChain
+    with replayed variates; the same variates through the device sampler must walk the same chains --
+    same number of accepted models at the same iterations, same final model / vpvs / noise bit for bit,
+    likelihoods within the forward-model tolerance, same proposal widths and counters."""
+    from bayhunter_b200 import SingleChain as sc, Targets
+    fx = np.load(os.path.join(golden_dir, "ref_chains_config1.npz"))
+    cls = {"rdispph": Targets.RayleighDispersionPhase, "prf": Targets.PReceiverFunction}
+    jt = Targets.JointTarget([cls[str(r)](fx["obs_%s_x" % r], fx["obs_%s_y" % r]) for r in fx["refs"]])
+    priors = dict(vs=(2.0, 5.0), z=(0, 60), layers=(1, 20), vpvs=(1.4, 2.1), mantle=None, mohoest=None,
+                  rfnoise_corr=(0.35, 0.75), rfnoise_sigma=(1e-5, 0.05), swdnoise_corr=0., swdnoise_sigma=(1e-5, 0.05))
+    ip = dict(iter_burnin=int(fx["iters"][0]), iter_main=int(fx["iters"][1]), propdist=(0.015, 0.015, 0.015, 0.005, 0.005),
+              acceptance=(40, 45), thickmin=0.1, lvz=None, hvz=None, rcond=1e-5)
+    C, ITER = fx["draws"].shape[0], fx["draws"].shape[1]
+    ens = sc.ChainEnsemble(jt, priors, ip, nchains=C, seed=1, max_accepted=ITER + 8)
+    L = ens.maxlayers
+    models = [np.concatenate((fx["init_model"][c, :fx["init_k"][c]], fx["init_model"][c, L:L + fx["init_k"][c]]))
+              for c in range(C)]
+    ens.init(models, fx["init_vpvs"], fx["init_noise"])
+    for it in range(ITER):
+        ens.force_draws(fx["draws"][:, it, :])
+        ens.run(1)
+    st = ens.state()
+    arr = ens.chain_arrays()
+    assert np.array_equal(st["nstored"], fx["n_accepted"])
+    assert np.array_equal(st["k"], fx["fin_k"])
+    for c in range(C):
+        k = int(fx["fin_k"][c])
+        assert np.array_equal(st["models"][c, :k], fx["fin_model"][c, :k]), c
+        assert np.array_equal(st["models"][c, L:L + k], fx["fin_model"][c, L:L + k]), c
+        n = int(fx["n_accepted"][c])
+        assert np.array_equal(arr["iters"][c, :n], fx["acc_iters"][c, :n].astype(np.int32)), c
+        rel = np.abs(arr["likes"][c, :n] - fx["acc_likes"][c, :n]) / np.maximum(1.0, np.abs(fx["acc_likes"][c, :n]))
+        assert rel.max() <= 2e-6, (c, rel.max())                                  # float32 chain arrays
+    assert np.array_equal(st["vpvs"], fx["fin_vpvs"]) and np.array_equal(st["noise"], fx["fin_noise"])
+    assert np.array_equal(st["propdist"], fx["fin_propdist"])
+    assert np.array_equal(st["accepted"], fx["fin_accepted"].astype(np.int64))
+    assert np.array_equal(st["proposed"], fx["fin_proposed"].astype(np.int64))
+    assert np.allclose(st["logL"], fx["fin_logL"], rtol=1e-6)
+    assert (st["iiter"] == int(fx["iters"][1])).all()
