@@ -98,13 +98,13 @@ def make_config(targets, priors, initparams, seed=0, max_accepted=None, nchains=
     if max_accepted is None:
         # The reference sizes its chain arrays as iterations * max(acceptance) / 100
         # (mcmcOptimizer.py:86-88) and dies with an IndexError when a chain accepts more.  Device
-        # memory is cheap: keep one row per iteration while the arrays stay below ~4 GB, else the
+        # memory is cheap: keep one row per iteration while the arrays stay below 16 GB, else the
         # reference's size plus a quarter -- but never more than `max_chain_bytes` (32 GB of the B200's
         # 180 GB) for the whole ensemble: beyond that accepted models are counted as overflow, not stored.
         iterations = c.iter_burnin + c.iter_main
         row_bytes = 4 * (2 * (c.layers_max + 1) + 3 * targets.ntargets + 4)
         n = int(nchains) if nchains is not None else int(initparams.get('nchains', 1))
-        if (iterations + 1) * row_bytes * n <= (4 << 30):
+        if (iterations + 1) * row_bytes * n <= (16 << 30):
             max_accepted = iterations + 1
         else:
             max_accepted = int(1.25 * iterations * np.max(initparams['acceptance']) / 100.) + 16
