@@ -351,7 +351,7 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
     // swd_spw_rg / swd_spw_rp / swd_spw_lg / swd_spw_lp: models per warp of one curve type (0 = rule above)
     const int w = key[8] == 'r' ? 0 : key[8] == 'l' ? 2 : -1, g = key[9] == 'g' ? 0 : key[9] == 'p' ? 1 : -1;
     if (w < 0 || g < 0) return set_err(BH_ERR_ARG, "unknown tunable");
-    if (value < 0 || value > (g == 0 ? 16 : 32) || (value & (value - 1))) return set_err(BH_ERR_ARG, "models per warp must be 0 or a power of two (<= 16 for group curves)");
+    if (value < 0 || value > (g == 0 ? 16 : 32)) return set_err(BH_ERR_ARG, "models per warp must be 0..32 (<= 16 for group curves)");
     e->spw_curve[w + g] = value;
   } else if (!strcmp(key, "swd_max_spec")) {
     if (value < 1 || value > 32) return set_err(BH_ERR_ARG, "swd_max_spec must be 1..32");
@@ -570,6 +570,25 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     }
     if (Sg == 0) Sg = S > 16 ? 16 : S;
     if (Sg > 16) Sg = 16;
+    // A grid a little above 12 warps per SM would take the 128-register build of the kernel (~10 % slower
+    // code).  Phase curves have spare lanes: a few more models per warp (up to 24, not a power of two) bring
+    // the grid back under that line -- 16 -> 23 at B = 8192 with four curves: 4.6 -> 4.34 ms.
+    if (e->searches_per_warp == 0 && e->nsm > 0) {
+      long long nph = 0, wgr = 0;
+      for (int w = 0; w < 2; ++w)
+        for (int c = 0; c < swl[w].ncurves; ++c) {
+          if (swl[w].igr[c]) wgr += (B + Sg - 1) / Sg; else nph += 1;
+        }
+      // a quarter of a warp per SM of slack: a grid that fills every slot leaves no room for the one-thread
+      // gate kernel and runs in two waves every other time (4.3 / 5.2 ms bimodal at 1770 of 1776 slots,
+      // stable 4.34 ms at 1738; profiles/r01_variants.txt)
+      const long long line = 12LL * e->nsm - e->nsm / 4;
+      const long long now = wgr + nph * ((B + S - 1) / S);
+      if (nph > 0 && now > line && S < 24) {
+        for (int s2 = S + 1; s2 <= 24; ++s2)
+          if (wgr + nph * ((B + s2 - 1) / s2) <= line) { S = s2; break; }
+      }
+    }
     // keep one warp's records + mailbox within ~24 KB of shared memory
     auto fit = [](int s_, int lc) { while (s_ > 1 && swd_smem_bytes(lc, s_) > 24 * 1024) s_ >>= 1; return s_; };
     if (swl[0].ncurves > 0 && swl[1].ncurves > 0 && e->concurrent) {

@@ -25,7 +25,7 @@
 // resident warps (= CTAs) per SM the register allocation must allow
 // Register budget of the instantiations that carry the Rayleigh code, as "resident warps (= CTAs)
 // per SM the allocation must allow":
-//   12 -> 147 registers: the faster code (~10 %) whenever the whole grid is resident anyway
+//   12 -> 147 registers: the faster code (~10 %) whenever the whole grid is resident anyway (<= 12 warps per SM)
 //   14 -> 128 registers, no spills: the whole grid of a full batch (~2048 warps on 148 SMs) is
 //         resident at once instead of leaving a second wave (4.65 -> 4.2 ms at B = 8192)
 // launch_one() picks per launch from the grid size (profiles/r01_variants.txt).
@@ -355,8 +355,9 @@ static void launch_one(const SwdLaunch& p, int warps, size_t smem, cudaStream_t 
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 1) nsm = 148;
   }
-  // the roomy build holds 13 warps per SM; a larger grid takes the 128-register build
-  if (warps > 13 * nsm) launch_inst<kDirect, kWave, BH_SWD_MIN_BLOCKS_RAYLEIGH_DENSE>(p, warps, smem, st);
+  // the roomy build holds 12 warps per SM (147 registers are allocated as 160 per thread); a larger grid
+  // takes the 128-register build (measured cliff between 1776 and 1792 warps on 148 SMs)
+  if (warps > 12 * nsm) launch_inst<kDirect, kWave, BH_SWD_MIN_BLOCKS_RAYLEIGH_DENSE>(p, warps, smem, st);
   else launch_inst<kDirect, kWave, BH_SWD_MIN_BLOCKS_RAYLEIGH>(p, warps, smem, st);
 }
 
