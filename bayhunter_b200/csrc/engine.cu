@@ -530,6 +530,24 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
         const long long d = warps > target ? warps - target : target - warps;
         if (bestd < 0 || d < bestd) { bestd = d; pick = i; }
       }
+      if (e->nsm > 0) {
+        // a pick that overflows even the dense build's resident wave (16 warps per SM) runs in two waves:
+        // prefer the largest candidate that, with its phase curves lifted to <= 24 models per warp, fits
+        // under the roomy build's line (B = 7168, four curves: 5.1 -> 4.1 ms)
+        auto grid = [&](int i, int sph) {
+          return nph * ((B + sph - 1) / sph) + ngr * ((B + cand[i][1] - 1) / cand[i][1]);
+        };
+        const long long line = 12LL * e->nsm - e->nsm / 4;
+        if (grid(pick, cand[pick][0]) > 16LL * e->nsm) {
+          long long bestw = -1;
+          for (int i = 0; i < 10; ++i) {
+            int sph = cand[i][0];
+            while (sph < 24 && grid(i, sph) > line) ++sph;
+            const long long w = grid(i, sph);
+            if (w <= line && w > bestw) { bestw = w; pick = i; }
+          }
+        }
+      }
       if (e->autotune && Sg == 0) {
         bh_engine::Tune& t = e->tune;
         if (t.B != B || t.base != pick) {              // new problem size: start over
