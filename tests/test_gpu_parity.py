@@ -528,3 +528,31 @@ def test_maximum_sizes_and_empty_batch(oracle):
     # B = 0: nothing to do, no error
     empty = eng.eval_host(rows[:0], nlay[:0], noise[:0])
     assert empty[0].size == 0 and empty[2].size == 0
+
+
+def test_skipped_models_do_not_disturb_their_neighbours():
+    """nlay = 0 marks a model to skip (the sampler's invalid proposals): it must come back invalid with the
+    sentinels, and every other model must get exactly the result it gets in a batch without the gaps --
+    for batch sizes that do not divide by the models-per-warp choice either."""
+    from bayhunter_b200 import Engine, TargetSpec, synthetic
+    rng = np.random.default_rng(23)
+    periods = np.linspace(1, 40, 12)
+    x_rf = synthetic.rf_time_axis(dict(n=201, dt=0.2, t0=-5.0))
+    specs = [TargetSpec("rdispph", periods, 3.5 + rng.normal(0, .1, 12), cov="exp"),
+             TargetSpec("ldispgr", periods, 3.5 + rng.normal(0, .1, 12), cov="exp"),
+             TargetSpec("prf", x_rf, rng.normal(0, .02, x_rf.size), cov="exp")]
+    B = 203
+    rows, nlay = synthetic.draw_batch(B, (2, 9), seed=3)
+    noise = synthetic.draw_noise(B, [s.ref for s in specs], seed=4)
+    eng = Engine(specs, B, rows.shape[1])
+    full = eng.eval_host(rows, nlay, noise, want_synth=True)
+    skip = rng.random(B) < 0.3
+    nl2 = np.where(skip, 0, nlay).astype(np.int32)
+    part = eng.eval_host(rows, nl2, noise, want_synth=True)
+    assert (part[2][skip] == 0).all() and (part[0][skip] == -1e15).all() and (part[1][skip] == 1e15).all()
+    keep = ~skip
+    assert np.array_equal(part[2][keep], full[2][keep])
+    assert np.array_equal(part[0][keep], full[0][keep])
+    assert np.array_equal(part[3][keep], full[3][keep], equal_nan=True)
+    sub = eng.eval_host(rows[keep], nlay[keep], noise[keep], want_synth=True)
+    assert np.array_equal(sub[0], full[0][keep]) and np.array_equal(sub[3], full[3][keep], equal_nan=True)
