@@ -258,6 +258,14 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
 #ifndef BH_LOVE_GROUP
 #define BH_LOVE_GROUP (BH_SWD_WIDE ? 4 : 1)
 #endif
+// 1: the compares of non-negative doubles against constants with a zero low word (floor of the
+// radicand, p < 16, p + q < 60) and the sign test k <= xk are integer compares on the high
+// words -- they leave the fp64 pipe, which bounds the layer loops (2 issue cycles per warp
+// instruction); the square root takes ONE coupled Newton step after the MUFU seed (2^-21)
+// and finishes sqrt and 1/sqrt with one residual correction each (10 fp64 instructions, was 13).
+#ifndef BH_SWD_LEAN
+#define BH_SWD_LEAN 1
+#endif
 constexpr int SWD_REC_FIELDS = 6;
 // Rayleigh record fields
 enum { RR_D = 0, RR_IA = 1, RR_IB = 2, RR_RHO = 3, RR_IRHO = 4, RR_TB2 = 5 };
@@ -305,9 +313,24 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
 #if defined(__CUDA_ARCH__)
   double s[N], y[N], g[N], hh[N], r[N], p[N], pm[N];
   bool osc[N];
-  BH_N(s[i] = (k + xk[i]) * fabs(k - xk[i]))
   // grazing (k == xk, reference: cosp = 1, w = d, x = 0): a floored radicand on
   // the oscillatory side gives cos(1e-100 d) = 1, sin(p)/r = d, r sin(p) = 1e-200 d
+#if BH_SWD_LEAN
+  // s >= 0: doubles order like their high words; k - xk is exactly +0 or at least one ulp of k
+  BH_N(double dk = k - xk[i]; s[i] = (k + xk[i]) * fabs(dk); osc[i] = __double2hiint(dk) <= 0)
+  BH_N(s[i] = fm::hi_lo(max(__double2hiint(s[i]), 0x16687e92), __double2loint(s[i])))      // hi word of 1e-200
+  BH_N(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i])))
+  // halving / doubling of normal numbers: exponent field arithmetic on the high word
+  BH_N(g[i] = s[i] * y[i]; hh[i] = fm::hi_lo(__double2hiint(y[i]) - 0x00100000, __double2loint(y[i])))
+  BH_N(r[i] = fma(-g[i], hh[i], 0.5))
+  BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))       // ~2^-40
+  BH_N(r[i] = fma(-g[i], g[i], s[i]))
+  BH_N(g[i] = fma(r[i], hh[i], g[i]))                                      // g = sqrt(s)
+  BH_N(hh[i] = fm::hi_lo(__double2hiint(hh[i]) + 0x00100000, __double2loint(hh[i])))
+  BH_N(r[i] = fma(-g[i], hh[i], 1.0))                  // g is final: the residual of g * hh is the error of hh alone
+  BH_N(hh[i] = fma(hh[i], r[i], hh[i]))                                    // hh = 1/sqrt(s)
+#else
+  BH_N(s[i] = (k + xk[i]) * fabs(k - xk[i]))
   BH_N(s[i] = (s[i] < 1.0e-200) ? 1.0e-200 : s[i]; osc[i] = k <= xk[i])
   BH_N(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i])))
   BH_N(g[i] = s[i] * y[i]; hh[i] = 0.5 * y[i])
@@ -317,6 +340,7 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
   BH_N(r[i] = fma(-g[i], g[i], s[i]))
   BH_N(g[i] = fma(r[i], hh[i], g[i]); hh[i] = hh[i] + hh[i])      // g = sqrt(s), hh = 1/sqrt(s)
+#endif
   BH_N(p[i] = g[i] * d[i]; pm[i] = osc[i] ? 0.0 : p[i])
   // exp(-pm) and sincos(p), step by step side by side.  With BH_P_SINCOS_COND the P half of a
   // Rayleigh layer (i = 0 of N = 2) takes its sincos only when some lane of the warp has an
@@ -365,11 +389,21 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   BH_N(double a = (q[i] & 1) ? cn[i] : sn[i]; double b = (q[i] & 1) ? sn[i] : cn[i];
        sn[i] = fm::hi_lo(__double2hiint(a) ^ ((q[i] & 2) << 30), __double2loint(a));
        cn[i] = fm::hi_lo(__double2hiint(b) ^ (((q[i] + 1) & 2) << 30), __double2loint(b)))
+#if BH_SWD_LEAN
+  BH_N(fac[i] = (__double2hiint(pm[i]) < 0x40300000) ? em[i] * em[i] : 0.0)      // pm >= 0: pm < 16
+#else
   BH_N(fac[i] = (pm[i] < 16.0) ? em[i] * em[i] : 0.0)
+#endif
   BH_N(ch[i] = fma(fac[i], 0.5, 0.5); sh[i] = fma(fac[i], -0.5, 0.5))
   BH_N(h[i].cs = osc[i] ? cn[i] : ch[i]; sh[i] = osc[i] ? sn[i] : sh[i])
+#if BH_SWD_LEAN
+  BH_N(h[i].sn_over_r = sh[i] * hh[i]; double rs = g[i] * sh[i];
+       h[i].r_sn = fm::hi_lo(__double2hiint(rs) ^ (osc[i] ? (int)0x80000000 : 0), __double2loint(rs));
+       h[i].ex = pm[i]; h[i].em = em[i])
+#else
   BH_N(h[i].sn_over_r = sh[i] * hh[i]; double rs = g[i] * sh[i]; h[i].r_sn = osc[i] ? -rs : rs;
        h[i].ex = pm[i]; h[i].em = em[i])
+#endif
 #else
   for (int i = 0; i < N; ++i) {
     double s = (k + xk[i]) * fabs(k - xk[i]);
@@ -403,8 +437,10 @@ BH_HD void sqrt_n(const double* sIn, double* out) {
   BH_N(g[i] = s[i] * y[i]; hh[i] = 0.5 * y[i])
   BH_N(r[i] = fma(-g[i], hh[i], 0.5))
   BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
+#if !BH_SWD_LEAN
   BH_N(r[i] = fma(-g[i], hh[i], 0.5))
   BH_N(g[i] = fma(g[i], r[i], g[i]); hh[i] = fma(hh[i], r[i], hh[i]))
+#endif
   BH_N(r[i] = fma(-g[i], g[i], s[i]))
   BH_N(out[i] = (sIn[i] < 1.0e-200) ? 0.0 : fma(r[i], hh[i], g[i]))
 #else
@@ -485,7 +521,11 @@ BH_HD DunkinLayer dunkin_from_terms(const double* rec, int fs, const HalfTerms& 
   double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
   double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
   double exa = P.ex + S.ex;
+#if BH_SWD_LEAN && defined(__CUDA_ARCH__)
+  double a0 = (__double2hiint(exa) < 0x404e0000) ? P.em * S.em : 0.0;     // exa >= 0: exa < 60
+#else
   double a0 = (exa < 60.0) ? P.em * S.em : 0.0;
+#endif
   double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
   double xy = x * y, xz = x * z, wy = w * y, wz = w * z;
   double gamm1 = gam - 1.0;
