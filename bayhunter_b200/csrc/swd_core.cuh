@@ -266,6 +266,11 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
 #ifndef BH_SWD_LEAN
 #define BH_SWD_LEAN 1
 #endif
+// 1: e * C(layer) through the rank-one structure of Dunkin's compound matrix (dunkin_apply_factored:
+// ~70 fp64 instructions per layer instead of ~100 for forming the 19 distinct entries and the 5x5 product)
+#ifndef BH_DUNKIN_FACTORED
+#define BH_DUNKIN_FACTORED 1
+#endif
 constexpr int SWD_REC_FIELDS = 6;
 // Rayleigh record fields
 enum { RR_D = 0, RR_IA = 1, RR_IB = 2, RR_RHO = 3, RR_IRHO = 4, RR_TB2 = 5 };
@@ -352,23 +357,23 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
 #endif
   double te[N], ts[N], fe[N], ft[N], re[N], rt[N], z[N], pe[N], ps[N], pc[N];
   int ne[N], q[N];
-  double sn[N], cn[N], hz[N], w1[N];
+  double sn[N], cn[N];
 #define BH_SC(...) if (i >= I0) { __VA_ARGS__; }
   BH_N(te[i] = fma(-pm[i], BH_K(K_LOG2E), BH_K(K_MAGIC)); BH_SC(ts[i] = fma(p[i], BH_K(K_TWO_OVER_PI), BH_K(K_MAGIC))))
   BH_N(ne[i] = __double2loint(te[i]); fe[i] = te[i] - BH_K(K_MAGIC);
        BH_SC(q[i] = __double2loint(ts[i]); ft[i] = ts[i] - BH_K(K_MAGIC)))
   BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_HI), -pm[i]); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_1), p[i])))
   BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_LO), re[i]); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_2), rt[i])))
-  BH_N(pe[i] = fma(BH_K_E13, re[i], BH_K_E12); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_3), rt[i])))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E11); BH_SC(z[i] = rt[i] * rt[i]))
+  BH_N(pe[i] = fma(BH_K_E13, re[i], BH_K_E12); BH_SC(z[i] = rt[i] * rt[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E11))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K_E10); BH_SC(ps[i] = fma(BH_K_S6, z[i], BH_K(K_S5)); pc[i] = fma(BH_K_C6, z[i], BH_K(K_C5))))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E9)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4))))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E8)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3))))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E7)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2))))
   BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E6)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S1)); pc[i] = fma(pc[i], z[i], BH_K(K_C1))))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E5)); BH_SC(sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); hz[i] = 0.5 * z[i]))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E4)); BH_SC(w1[i] = 1.0 - hz[i]; pc[i] = z[i] * z[i] * pc[i]))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E3)); BH_SC(cn[i] = w1[i] + (((1.0 - w1[i]) - hz[i]) + pc[i])))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E5)); BH_SC(sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); pc[i] = fma(z[i], pc[i], -0.5)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E4)); BH_SC(cn[i] = fma(z[i], pc[i], 1.0)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E3)))
   BH_N(pe[i] = fma(pe[i], re[i], 0.5))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
@@ -556,6 +561,54 @@ BH_HD DunkinLayer dunkin_from_terms(const double* rec, int fs, const HalfTerms& 
   return m;
 }
 
+// e <- e * C(layer) without forming C.  With A = a0 - cosp cosq, X = x z, W = w y the block of rows /
+// columns (1, 3, 5) of Dunkin's matrix (:1032-1067) is
+//     cosp cosq * I + A uA vA^T + X uX vX^T + W uW vW^T
+//     uA = (1, -(2 gam - 1) rho, gammk gamm1 rho^2)     vA = -(2 gam gamm1, (2 gam - 1) / rho, 2 k^2 / rho^2)
+//     uX = (1, -2 gam rho, gam gammk rho^2)             vX = -(gam gammk, gammk / rho, 1 / rho^2)
+//     uW = (k^2, -2 k^2 gamm1 rho, gamm1^2 rho^2)       vW = -(gamm1^2, gamm1 / rho, k^2 / rho^2)
+// (gam = gammk k^2), and the entries that couple them with components 2 and 4 are built from the same vectors:
+//     rows 2, 4 -> columns (1, 3, 5):  -cosp z rho vX + cosq w rho vW,   -cosp y rho vW + cosq x rho vX
+//     rows (1, 3, 5) -> columns 2, 4:  (cosp y uW - cosq x uX) / rho,    (cosp z uX - cosq w uW) / rho
+// so the product needs three dot products e.u, three scaled sums and two short rows.  Same algebra as
+// dunkin_from_terms + BH_DUNKIN_APPLY, re-associated (values agree to a few ulp of the vector norm).
+BH_HD void dunkin_apply_factored(const double* rec, int fs, const HalfTerms& P, const HalfTerms& S, double k2,
+                                 double iomega2, double& e0, double& e1, double& e2, double& e3, double& e4) {
+  const double rho = rec[RR_RHO * fs], ri = rec[RR_IRHO * fs];
+  const double gk = rec[RR_TB2 * fs] * iomega2;          // gammk = 2 (b/omega)^2
+  const double gam = gk * k2;
+  const double gm1 = gam - 1.0;
+  const double tw = gam + gm1;
+  const double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
+  const double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
+  const double exa = P.ex + S.ex;
+#if BH_SWD_LEAN && defined(__CUDA_ARCH__)
+  const double a0 = (__double2hiint(exa) < 0x404e0000) ? P.em * S.em : 0.0;     // exa >= 0: exa < 60
+#else
+  const double a0 = (exa < 60.0) ? P.em * S.em : 0.0;
+#endif
+  const double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
+  const double A = a0 - cpcq, X = x * z, W = w * y;
+  const double f3 = e2 * rho, f5 = e4 * (rho * rho);
+  const double ggm1 = gk * gm1, gmgk = gam * gk, gm1sq = gm1 * gm1, k2g1 = k2 * gm1;
+  const double dA = fma(ggm1, f5, fma(-tw, f3, e0));
+  const double dX = fma(gmgk, f5, fma(-2.0 * gam, f3, e0));
+  const double dW = fma(gm1sq, f5, fma(-2.0 * k2g1, f3, k2 * e0));
+  const double sA = A * dA;
+  const double sX = fma(-rho, fma(cpz, e1, -(cqx * e3)), X * dX);
+  const double sW = fma(rho, fma(cqw, e1, -(cpy * e3)), W * dW);
+  const double t1 = fma(gm1sq, sW, fma(gmgk, sX, (2.0 * gam * gm1) * sA));
+  const double t3 = fma(gm1, sW, fma(gk, sX, tw * sA));
+  const double t5 = fma(k2, sW, fma(2.0 * k2, sA, sX));
+  const double n0 = fma(cpcq, e0, -t1);
+  const double n2 = fma(-ri, t3, cpcq * e2);
+  const double n4 = fma(-(ri * ri), t5, cpcq * e4);
+  const double n1 = fma(ri, fma(cpy, dW, -(cqx * dX)), fma(cpcq, e1, -((x * y) * e3)));
+  const double n3 = fma(ri, fma(cpz, dX, -(cqw * dW)), fma(cpcq, e3, -((w * z) * e1)));
+  const double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
+  e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
+}
+
 // NL consecutive layers l0, l0-1, ... at once: 2*NL half-term chains side by side
 template <int NL>
 BH_HD void dunkin_layers_n(const double* rec, int fs, int ls, int l0, double wvno, double wvno2, double omega,
@@ -620,9 +673,17 @@ BH_HD double secular_rayleigh_rec(const double* rec, int fs, int ls, int L, doub
   int l = L - 2;
 #pragma unroll 1
   for (int r = BH_SWD_WIDE ? ((L - 1) & 1) : (L - 1); r > 0; --r, --l) {
+#if BH_DUNKIN_FACTORED
+    const double* rl = rec + l * ls;
+    double xk[2] = {omega * rl[RR_IA * fs], omega * rl[RR_IB * fs]}, dd[2] = {rl[RR_D * fs], rl[RR_D * fs]};
+    HalfTerms h[2];
+    half_terms_n<2>(wvno, xk, dd, h);
+    dunkin_apply_factored(rl, fs, h[0], h[1], wvno2, iomega2, e0, e1, e2, e3, e4);
+#else
     DunkinLayer m;
     dunkin_layers_n<1>(rec, fs, ls, l, wvno, wvno2, omega, iomega2, &m);
     BH_DUNKIN_STEP(m)
+#endif
   }
 #if BH_SWD_WIDE
 #pragma unroll 1
