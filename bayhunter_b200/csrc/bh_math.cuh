@@ -109,15 +109,17 @@ BH_HD void sqrt_rsqrt(double x, double* s, double* rs) {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // one coupled Newton step on the 2^-21 seed (-> 2^-40), then one residual correction each
+  // for sqrt and 1/sqrt (sqrt <= 0.5 ulp + rounding, 1/sqrt <= 1.5 ulp)
   double g = x * y, h = 0.5 * y;
   double r = fma(-g, h, 0.5);
   g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
   double d = fma(-g, g, x);
   g = fma(d, h, g);
+  h = h + h;
+  r = fma(-g, h, 1.0);
   *s = g;
-  *rs = h + h;
+  *rs = fma(h, r, h);
 #else
   *s = sqrt(x);
   *rs = 1.0 / *s;

@@ -18,6 +18,7 @@
 // (model, frequency) items and only reads those tables.
 #pragma once
 #include "bh_common.cuh"
+#include "bh_math.cuh"
 
 namespace bh {
 
@@ -147,18 +148,58 @@ BH_HD bool rf_decomp_consts(double u, double nsv, double sigma, double* m) {
   return on;
 }
 
+// Complex helpers of the per-(layer, frequency) inner loop.  On the device they use the straight-line
+// reciprocal / square root / exp / sincos of bh_math.cuh (<= 2 ulp, no slow-path branches; arguments here
+// are finite, normal and of modest size: |Im| of a phase <= a few hundred, Re <= 0 up to attenuation);
+// the host build (tests/host_sim) keeps libm.  BH_RF_FAST=0 restores the CUDA library versions.
+#ifndef BH_RF_FAST
+#define BH_RF_FAST 1
+#endif
+BH_HD cd rf_crecip(cd a) {
+#if BH_RF_FAST && defined(__CUDA_ARCH__)
+  double d = fm::rcp(cnorm(a));
+  return mk(a.re * d, -a.im * d);
+#else
+  return crecip(a);
+#endif
+}
+BH_HD cd rf_csqrt(cd z) {
+#if BH_RF_FAST && defined(__CUDA_ARCH__)
+  double x = z.re, y = z.im;
+  if (x == 0.0 && y == 0.0) return mk(0.0, y);
+  double r, rs, t, ts;
+  fm::sqrt_rsqrt(fma(x, x, y * y), &r, &rs);
+  fm::sqrt_rsqrt(0.5 * (r + fabs(x)), &t, &ts);
+  double h = 0.5 * ts;                                   // 1 / (2 t)
+  if (x >= 0.0) return mk(t, y * h);
+  return mk(fabs(y) * h, copysign(t, y));
+#else
+  return csqrt_p(z);
+#endif
+}
+BH_HD cd rf_cexp(cd z) {
+#if BH_RF_FAST && defined(__CUDA_ARCH__)
+  double s, c;
+  fm::sincos_cw(z.im, &s, &c);
+  double e = fm::exp_small(z.re < -700.0 ? -700.0 : z.re);     // below: 1e-304 stands for 0
+  return mk(e * c, e * s);
+#else
+  return cexp_d(z);
+#endif
+}
+
 // Phase terms of one layer at angular frequency w (greens.cpp:533-548):
 // complex-Q velocities v*(1 + lgw/(pi*Q) + i/(2Q)), principal-branch vertical
 // slownesses, e = exp(-i*w*d*slowness).
 BH_HD void rf_phase(const RfLayer& L, double u2, double w, double lgw, cd* ep, cd* es) {
   cd vpc = L.vp * mk(1.0 + lgw * L.cqp, L.bqp);
   cd vsc = L.vs * mk(1.0 + lgw * L.cqs, L.bqs);
-  cd plc = csqrt_p(crecip(vpc * vpc) - mk(u2, 0.0));
-  cd slc = csqrt_p(crecip(vsc * vsc) - mk(u2, 0.0));
+  cd plc = rf_csqrt(rf_crecip(vpc * vpc) - mk(u2, 0.0));
+  cd slc = rf_csqrt(rf_crecip(vsc * vsc) - mk(u2, 0.0));
   double wd = -w * L.h;
   // (0, wd) * plc = (-wd*plc.im, wd*plc.re)
-  *ep = cexp_d(mk(-wd * plc.im, wd * plc.re));
-  *es = cexp_d(mk(-wd * slc.im, wd * slc.re));
+  *ep = rf_cexp(mk(-wd * plc.im, wd * plc.re));
+  *es = rf_cexp(mk(-wd * slc.im, wd * slc.re));
 }
 
 // One (model, frequency) item: reflectivity recursion over the nlay-1 finite
@@ -187,7 +228,7 @@ BH_HD cm2 rf_transfer(const RfLayer* lay, const cm2* coef, const cm2& h2, int nl
     nb.a21 = nt.a21 * eps; nb.a22 = nt.a22 * ess;
     cm2 r = mmul(cn[0], nb);                            // rd[i+1]*nb[i]
     cd m11 = mk(1.0, 0.0) - r.a11, m12 = -r.a12, m21 = -r.a21, m22 = mk(1.0, 0.0) - r.a22;
-    cd dinv = crecip(m11 * m22 - m12 * m21);
+    cd dinv = rf_crecip(m11 * m22 - m12 * m21);
     cm2 inv;
     inv.a11 = dinv * m22; inv.a12 = -(dinv * m12);
     inv.a21 = -(dinv * m21); inv.a22 = dinv * m11;
