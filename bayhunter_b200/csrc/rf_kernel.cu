@@ -6,8 +6,8 @@
 //                       intra-warp divergence at model boundaries).  Runs the
 //                       reflectivity recursion and the spectral division and
 //                       writes the filtered spectrum crf[b][0..N/2].
-//   rf_synth_kernel     one CTA per model: Hermitian extension, radix-2
-//                       inverse FFT in shared memory, first ndata samples out.
+//   rf_synth_kernel     one CTA per model: real inverse FFT of the Hermitian spectrum as one
+//                       half-size complex radix-2 transform in shared memory, first ndata samples out.
 // The spectrum (B x (N/2+1) x 16 B) stays L2-resident between the two.
 #include "kernels.h"
 
@@ -50,40 +50,49 @@ rf_spectrum_kernel(RfLaunch p) {
   }
 }
 
-// radix-2 decimation-in-time inverse transform, sign +1, total scale 1/N
-// (fork.cpp:10-60 with signi = +1 and iftr's second 1/sqrt(N), greens.cpp:147,157)
+// Inverse transform of the Hermitian spectrum (iftr, greens.cpp:136-158: Hermitian extension, radix-2
+// transform with sign +1 and total scale 1/N, real part -- fork.cpp:10-60).  The N real samples come out
+// of ONE complex transform of half the size: with M = N/2 and T[k] = exp(2 pi i k / N),
+//     Z[k] = (X[k] + conj X[M-k]) + i T[k] (X[k] - conj X[M-k]),  k < M
+//     z = sum_k Z[k] exp(2 pi i k m / M)  =>  x[2m] = Re z[m],  x[2m+1] = Im z[m]
+// (taking the real part of the reference's full transform is the same as using Re X[0], Re X[M]).
+// Half the butterflies, one stage fewer, and a quarter of the sincos calls of the full-size transform.
 __global__ void rf_synth_kernel(RfLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* x = reinterpret_cast<cd*>(smem_raw);
   const int N = p.k.nsamp;
-  const int nfreq = N / 2 + 1;
+  const int M = N / 2;
+  const int nfreq = M + 1;
   const int b = blockIdx.x;
   const cd* __restrict__ spec = p.spec + (size_t)b * nfreq;
-  int logn = 0;
-  while ((1 << logn) < N) ++logn;
-  // Hermitian extension + bit reversal (iftr, greens.cpp:149-152)
-  const int nact = p.nact;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const int k = (i <= N / 2) ? i : N - i;
-    cd v = mk(0.0, 0.0);
-    if (k < nact) v = (i <= N / 2) ? spec[k] : cconj(spec[k]);
-    int r = (int)(__brev((unsigned)i) >> (32 - logn));
-    x[r] = v;
-  }
-  // twiddles exp(+i pi k / (N/2)), k < N/2, once per CTA (the reference recomputes exp() inside
-  // its butterfly loops, fork.cpp:40-55; same values)
-  cd* tw = x + N;
-  for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
+  int logm = 0;
+  while ((1 << logm) < M) ++logm;
+  // twiddles T[k], k < M, once per CTA: a quarter turn is a swap, T[k + M/2] = i T[k]
+  // (the reference recomputes exp() inside its butterfly loops, fork.cpp:40-55; same values)
+  cd* tw = x + M;
+  for (int k = threadIdx.x; k < (M + 1) / 2; k += blockDim.x) {
     double sw, cw;
-    sincospi((double)k / (double)(N / 2), &sw, &cw);
+    sincospi(2.0 * (double)k / (double)N, &sw, &cw);
     tw[k] = mk(cw, sw);
+    if (M >= 2) tw[k + M / 2] = mk(-sw, cw);
   }
   __syncthreads();
-  for (int l = 1, sh = logn - 1; l < N; l <<= 1, --sh) {
-    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+  const int nact = p.nact;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    cd a = mk(0.0, 0.0), c = mk(0.0, 0.0);
+    if (k < nact) a = spec[k];
+    if (M - k < nact) c = cconj(spec[M - k]);
+    if (k == 0) { a.im = 0.0; c.im = 0.0; }
+    const cd e = a + c, o = (a - c) * tw[k];
+    const int r = logm ? (int)(__brev((unsigned)k) >> (32 - logm)) : 0;
+    x[r] = mk(e.re - o.im, e.im + o.re);
+  }
+  __syncthreads();
+  for (int l = 1, sh = logm - 1; l < M; l <<= 1, --sh) {
+    for (int t = threadIdx.x; t < M / 2; t += blockDim.x) {
       int m = t & (l - 1);
       int i = ((t - m) << 1) + m;
-      cd wv = tw[m << sh];                      // exp(i pi m / l) = tw[m * (N/2) / l]
+      cd wv = tw[(m << sh) << 1];               // exp(i pi m / l) = T[m * M / l]
       cd a = x[i], bb = wv * x[i + l];
       x[i] = a + bb;
       x[i + l] = a - bb;
@@ -92,7 +101,10 @@ __global__ void rf_synth_kernel(RfLaunch p) {
   }
   const double scale = 1.0 / (double)N;
   double* __restrict__ out = p.out + (size_t)b * p.out_stride + p.out_off;
-  for (int i = threadIdx.x; i < p.ndata; i += blockDim.x) out[i] = x[i].re * scale;
+  for (int i = threadIdx.x; i < p.ndata; i += blockDim.x) {
+    const cd v = x[i >> 1];
+    out[i] = ((i & 1) ? v.im : v.re) * scale;
+  }
   if (threadIdx.x == 0 && p.tstatus) {
     int nl = p.nlay[b];
     p.tstatus[(size_t)b * kMaxTargets + p.target_id] = (nl >= 2) ? 1 : 0;
@@ -126,10 +138,10 @@ void launch_rf_spectrum(const RfLaunch& p, cudaStream_t st) {
 void launch_rf_synth(const RfLaunch& p, cudaStream_t st) {
   if (p.B <= 0) return;
   const int N = p.k.nsamp;
-  int threads = N / 2;
+  int threads = N / 4;                                              // one butterfly of the half-size transform each
   if (threads > 512) threads = 512;
   if (threads < 32) threads = 32;
-  const size_t smem = sizeof(cd) * ((size_t)N + (size_t)N / 2);     // samples + twiddles
+  const size_t smem = sizeof(cd) * ((size_t)N / 2 + (size_t)N / 2 + 1);   // packed samples + twiddles
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(rf_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
