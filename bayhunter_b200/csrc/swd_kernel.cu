@@ -225,7 +225,10 @@ swd_kernel(SwdLaunch p) {
       cnt = 1;
       if (want > 1) {
         int rank = __popc(bracket & ((1u << lane) - 1u));
-        int add = extra / nbr + (rank < (extra % nbr) ? 1 : 0);
+        // extra / nbr and extra % nbr for 0 <= extra <= 32, 1 <= nbr <= 32: (extra + 0.5) / nbr stays at least
+        // 1/64 away from every integer, far beyond the error of the approximate fp32 quotient
+        const int quo = __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr));
+        int add = quo + (rank < (extra - quo * nbr) ? 1 : 0);
         cnt += add;
         if (cnt > max_spec) cnt = max_spec;
       }
