@@ -58,15 +58,6 @@ struct WarpShared {
   double tab[SWD_TAB_ROWS * 32];   // Neville tableaus, one column per lane
 };
 
-__device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    unsigned n = __shfl_up_sync(0xffffffffu, v, d);
-    if (lane >= d) v += n;
-  }
-  return v;
-}
-
 // kDirect: every chain evaluates only its own next candidate (no speculation, no
 // dealing, no mailbox traffic) -- the mode for large batches, where all 32 lanes
 // of a warp own a chain anyway.  Otherwise spare lanes are dealt to the chains
@@ -218,37 +209,40 @@ swd_kernel(SwdLaunch p) {
     }
     ++rounds;
     unsigned bracket = __ballot_sync(0xffffffffu, want > 1);
-    int nact = __popc(active), nbr = __popc(bracket);
-    int extra = 32 - nact;
+    const int nact = __popc(active), nbr = __popc(bracket);
+    const int extra = 32 - nact;
+    // Lanes per chain: 1 for a chain that refines a root; the spare lanes are dealt evenly to the chains
+    // that walk a bracket (quo or quo + 1 more each, at most max_spec in all).  Counts and their prefix
+    // sums follow in closed form from the two ballots -- no shuffle scan on the round's critical path.
+    //   extra / nbr and extra % nbr for 0 <= extra <= 32, 1 <= nbr <= 32: (extra + 0.5) / nbr stays at least
+    //   1/64 away from every integer, far beyond the error of the approximate fp32 quotient
+    const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
+    const int rem = extra - quo * nbr;
+    const int per = quo + 1;                               // lanes of a walking chain of rank >= rem
+    const bool capped = per >= max_spec;
+    const unsigned below = (1u << lane) - 1u;
+    const int rank = __popc(bracket & below);
     int cnt = 0;
     if (want > 0) {
       cnt = 1;
-      if (want > 1) {
-        int rank = __popc(bracket & ((1u << lane) - 1u));
-        // extra / nbr and extra % nbr for 0 <= extra <= 32, 1 <= nbr <= 32: (extra + 0.5) / nbr stays at least
-        // 1/64 away from every integer, far beyond the error of the approximate fp32 quotient
-        const int quo = __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr));
-        int add = quo + (rank < (extra - quo * nbr) ? 1 : 0);
-        cnt += add;
-        if (cnt > max_spec) cnt = max_spec;
-      }
+      if (want > 1) cnt = min(per + (rank < rem ? 1 : 0), max_spec);
       ws->c[lane] = search_pending_c(s);
       ws->clow[lane] = s.clow;
       ws->omega[lane] = s.omega;
       ws->stage[lane] = s.stage;
       ws->idir[lane] = s.idir;
     }
-    unsigned incl = warp_incl_scan((unsigned)cnt, lane);
-    unsigned excl = incl - cnt;
-    unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    // walking chains below this lane hold rank * per + min(rank, rem) lanes (or rank * max_spec when capped)
+    const unsigned excl = (unsigned)(__popc(active & below) - rank + (capped ? rank * max_spec : rank * per + min(rank, rem)));
+    const unsigned total = (unsigned)(nact - nbr + (capped ? nbr * max_spec : nbr * per + min(nbr, rem)));
     unsigned startmask = __reduce_or_sync(0xffffffffu, cnt > 0 ? (1u << excl) : 0u);
     if (cnt > 0) ws->owner_at[excl] = lane;
     __syncwarp();
 
     // ---- phase B: every dealt lane evaluates one candidate ----
     if ((unsigned)lane < total) {
-      unsigned below = startmask & (0xffffffffu >> (31 - lane));
-      int start = 31 - __clz(below);
+      unsigned starts = startmask & (0xffffffffu >> (31 - lane));
+      int start = 31 - __clz(starts);
       int i = lane - start;
       int own = ws->owner_at[start];
       double omega = ws->omega[own];
