@@ -423,9 +423,20 @@ def main():
         dom_s = kmean[dom] * 1e-3
         fp64_peak = 148 * 64 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12   # DFMA/clk/SM * 2 flop
         traffic = None
+        pipe = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get(cfg, {}).get(dom + "_kernel")
+            pp = tr.get("fp64_pipe", {}).get(cfg)
+            if pp and dom == "swd":
+                # the fp64 pipe of a sub-partition takes one warp instruction per 2 cycles: instructions of the
+                # profiled launch (same workload) against the pipe cycles of the LIVE launch duration and clock
+                mhz = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+                pipe = {"busy_ncu": pp["busy_pct_ncu"] / 100.0,
+                        "busy_live": pp["fp64_warp_instructions"] * 2.0 / (148 * 4 * mhz * 1e6 * dom_s),
+                        "fp64_warp_instructions_per_launch": pp["fp64_warp_instructions"],
+                        "source": "profiles/traffic.json (ncu --set full capture of the same workload); busy_live = "
+                                  "fp64 warp instructions x 2 cycles / (592 sub-partitions x SM clock x live kernel time)"}
         except Exception:
             pass
         line = {
@@ -450,7 +461,8 @@ def main():
                      "peak_source": "148 SM x 64 DFMA/clk x 2 x sm_max_mhz; DFMA issue rate measured (tools/micro/fp64_latency.cu: "
                                     "1 warp-DFMA per 2 cycles per sub-partition), clock nominal",
                      "step_flops": flops, "step_tflops": flops / (total_ms / K * 1e-3) / 1e12,
-                     "secular_evals_per_step": counts[0] / K, "secular_evaluated_per_step": counts[1] / K},
+                     "secular_evals_per_step": counts[0] / K, "secular_evaluated_per_step": counts[1] / K,
+                     "pipe": pipe},
             "kernel_ms": kmean,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,

@@ -48,7 +48,21 @@ for kern, short in (("swd", "swd_kernel"), ("rf", "rf_spectrum")):
         i = h.index(key); v = float(vals[i].replace(",", "")); u = units[i].lower()
         tb += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
     traffic[short + ("_kernel" if kern == "rf" else "")] = int(tb)
+    if kern == "swd":
+        # fp64 pipe: ncu's own utilisation figure and the executed fp64 warp instructions of the launch
+        i = h.index("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+        pipe = {"busy_pct_ncu": float(vals[i].replace(",", ""))}
+        tot = 0; share = 0.0
+        for line in hist.splitlines():
+            t = line.split()
+            if line.startswith("warp instructions executed:"): tot = int(t[-1])
+            elif len(t) >= 2 and t[0] in ("DFMA", "DMUL", "DADD", "DSETP"): share += float(t[1].rstrip("%"))
+        pipe["fp64_warp_instructions"] = int(tot * share / 100.0)
+        pipe["warp_instructions"] = tot
 tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in this directory (bytes)",
-      "joint5": {"swd_kernel": traffic["swd_kernel"], "rf_spectrum_kernel": traffic["rf_spectrum_kernel"]}}
+      "joint5": {"swd_kernel": traffic["swd_kernel"], "rf_spectrum_kernel": traffic["rf_spectrum_kernel"]},
+      "fp64_pipe": {"_comment": "swd_kernel, same capture: sm__pipe_fp64_cycles_active (% of peak) and executed DFMA+DMUL+DADD+DSETP warp "
+                                "instructions per launch (each occupies the pipe of its sub-partition for 2 cycles)",
+                    "joint5": pipe}}
 json.dump(tj, open(os.path.join(P, "traffic.json"), "w"), indent=2)
 print(open(os.path.join(P, rnd + "_launch_shares.txt")).read()); print(tj)
