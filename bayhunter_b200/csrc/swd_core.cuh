@@ -364,16 +364,15 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
        BH_SC(q[i] = __double2loint(ts[i]); ft[i] = ts[i] - BH_K(K_MAGIC)))
   BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_HI), -pm[i]); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_1), p[i])))
   BH_N(re[i] = fma(-fe[i], BH_K(K_LN2_LO), re[i]); BH_SC(rt[i] = fma(-ft[i], BH_K(K_PIO2_2), rt[i])))
-  BH_N(pe[i] = fma(BH_K_E13, re[i], BH_K_E12); BH_SC(z[i] = rt[i] * rt[i]))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E11))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K_E10); BH_SC(ps[i] = fma(BH_K_S6, z[i], BH_K(K_S5)); pc[i] = fma(BH_K_C6, z[i], BH_K(K_C5))))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E9)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4))))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E8)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3))))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E7)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2))))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E6)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S1)); pc[i] = fma(pc[i], z[i], BH_K(K_C1))))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E5)); BH_SC(sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); pc[i] = fma(z[i], pc[i], -0.5)))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E4)); BH_SC(cn[i] = fma(z[i], pc[i], 1.0)))
-  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_E3)))
+  // exp(r) = 1 + r + r^2 Q(r), Q of degree 9 (bh_math.cuh: exp_small)
+  BH_N(pe[i] = fma(BH_K_Q9, re[i], BH_K_Q8); BH_SC(z[i] = rt[i] * rt[i]))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q7)); BH_SC(ps[i] = fma(BH_K_S6, z[i], BH_K(K_S5)); pc[i] = fma(BH_K_C6, z[i], BH_K(K_C5))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q6)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S4)); pc[i] = fma(pc[i], z[i], BH_K(K_C4))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q5)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S3)); pc[i] = fma(pc[i], z[i], BH_K(K_C3))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q4)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S2)); pc[i] = fma(pc[i], z[i], BH_K(K_C2))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q3)); BH_SC(ps[i] = fma(ps[i], z[i], BH_K(K_S1)); pc[i] = fma(pc[i], z[i], BH_K(K_C1))))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q2)); BH_SC(sn[i] = fma(rt[i] * z[i], ps[i], rt[i]); pc[i] = fma(z[i], pc[i], -0.5)))
+  BH_N(pe[i] = fma(pe[i], re[i], BH_K(K_Q1)); BH_SC(cn[i] = fma(z[i], pc[i], 1.0)))
   BH_N(pe[i] = fma(pe[i], re[i], 0.5))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
