@@ -184,6 +184,24 @@ def test_rf_plugin_random_models(oracle):
             assert np.abs(y - yo).max() / np.abs(yo).max() <= 1e-9, (it, ref, n)
 
 
+def test_rf_short_and_odd_traces(oracle):
+    """The real inverse transform runs as one half-size complex transform: the smallest transform sizes
+    (nsamp = 4 ... 256), odd sample counts and both wave types against the oracle."""
+    from bayhunter_b200 import RFminiModRF, synthetic
+    rng = np.random.default_rng(16)
+    for n in (2, 3, 5, 9, 17, 33, 100, 127):
+        h, vs = synthetic.draw_model(rng, int(rng.integers(2, 8)))
+        vp = vs * 1.73
+        rho = vp * 0.32 + 0.77
+        for ref in ("prf", "srf"):
+            x = -1.0 + 0.25 * np.arange(n)
+            plug = RFminiModRF(x, ref)
+            t, y = plug.run_model(h, vp, vs, rho)
+            _, yo = oracle.recfunc(h, vp, vs, rho, x, wtype="SV" if ref == "srf" else "P")
+            assert y.shape == yo.shape == (n,)
+            assert np.abs(y - yo).max() <= 1e-9 * max(np.abs(yo).max(), 1e-300), (n, ref)
+
+
 def _make_targets(refs, periods, rf, rng, laws=None):
     """Observed data = st3 truth + noise; returns (engine specs, oracle targets)."""
     from bayhunter_b200 import TargetSpec, gauss_corr_inverse
