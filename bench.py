@@ -202,7 +202,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg_description(cfg, nev, c), "sample_models_per_step": nev},
+        # the same workload as the b200 arm; each step evaluates a bounded sample of it
+        "config": {"workload": cfg_description(cfg, args.chains_per_gpu or synthetic.CONFIGS[cfg]["B"], c),
+                   "sample_models_per_step": nev},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
                          "sample": last["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
