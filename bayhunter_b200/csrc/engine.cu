@@ -522,6 +522,14 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       const long long chains = (long long)B * (nph + 2 * ngr);
       long long target = chains / 14;
       if (target > 2400) target = 2400;
+      // small batches: the chains are the critical path and the machine is far from full -- one warp per SM
+      // sub-partition (as long as a warp keeps two chains) before chains are packed 14 to a warp
+      // (profiles/r01_variants.txt: joint5 B = 256 / 512 / 1024: 1.81 -> 1.49 / 1.58 / 1.72 ms)
+      if (e->nsm > 0) {
+        long long fill = 4LL * e->nsm;
+        if (fill > chains / 2) fill = chains / 2;
+        if (target < fill) target = fill;
+      }
       static const int cand[][2] = {{32, 16}, {16, 16}, {16, 8}, {8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {2, 1}, {1, 1}};
       int pick = 9;
       long long bestd = -1;
