@@ -120,7 +120,7 @@ struct bh_engine {
   // tunables
   int searches_per_warp = 0;  // phase-velocity curves; 0 = auto
   int group_spw = 0;          // group-velocity curves; 0 = half of the above
-  int max_spec = 8;
+  int max_spec = 16;   // candidates per walking chain and round (8 -> 16: -3..5 % at B <= 512, neutral for a full batch)
   int spw_curve[4] = {0, 0, 0, 0};   // per curve type override: Rayleigh group, Rayleigh phase, Love group, Love phase
   int split_waves = 0;        // 1: Rayleigh and Love curves in separate launches (two streams)
   int rayleigh_sm_pct = 0;    // mixed launch: share of the SMs dedicated to the Rayleigh items (0 = no partition)
