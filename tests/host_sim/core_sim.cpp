@@ -22,6 +22,18 @@ uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 
 extern "C" {
 
+// Secular values of n trial phase velocities for one model at one period, in the formulation this
+// library was built with (device formulation, or the Fortran's operation order under
+// BH_SECULAR_REFERENCE_ORDER).
+void swd_sim_secular(const float* rows4, int nlayer, int wave, double omega, int n, const double* c, double* out) {
+  std::vector<LayerRow> rows(nlayer);
+  for (int i = 0; i < nlayer; ++i) {
+    rows[i].x = rows4[4 * i]; rows[i].y = rows4[4 * i + 1];
+    rows[i].z = rows4[4 * i + 2]; rows[i].w = rows4[4 * i + 3];
+  }
+  for (int j = 0; j < n; ++j) out[j] = secular(wave, rows.data(), 1, nlayer, omega / c[j], omega);
+}
+
 // One dispersion curve for one model.  rows: (d, vp, vs, rho) REAL*4 x nlayer.
 // spec_mode: 0 -> one candidate per round (reference order), k > 0 -> fixed k
 // speculative bracket candidates per round, < 0 -> random 1..32 per round.

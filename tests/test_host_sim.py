@@ -127,6 +127,40 @@ def test_device_formulation_of_secular_functions(oracle, host_sim):
     assert same_count >= 0.98 * total
 
 
+def test_secular_values_of_the_device_formulation(host_sim, host_sim_reforder):
+    """The secular functions as the kernels evaluate them -- records of reciprocals, branch-free half
+    terms, Rayleigh layers applied through the rank-one structure of Dunkin's matrix without forming it
+    (dunkin_apply_factored), power-of-two rescaling -- against the Fortran-order functions on the same
+    models, periods and trial velocities: normalised values equal to rounding, signs equal wherever the
+    value is not itself at rounding level."""
+    from bayhunter_b200 import synthetic
+    rng = np.random.default_rng(21)
+    worst = {1: 0.0, 2: 0.0}
+    nsign = 0
+    for it in range(400):
+        k = int(rng.integers(1, 31))
+        h, vs = synthetic.draw_model(rng, k)
+        if it % 5 == 0:
+            vs = rng.permutation(vs)                   # low-velocity zones
+        vp = vs * rng.uniform(1.4, 2.1)
+        rows = np.ascontiguousarray(np.stack([h, vp, vs, vp * 0.32 + 0.77], 1), dtype=np.float32)
+        omega = 2 * np.pi / 10 ** rng.uniform(-0.3, 1.8)
+        c = np.ascontiguousarray(rng.uniform(0.8 * vs.min(), 1.001 * vs.max(), 16))
+        for wave in (1, 2):
+            a = np.zeros(c.size); b = np.zeros(c.size)
+            for sim, out in ((host_sim, a), (host_sim_reforder, b)):
+                sim.swd_sim_secular(rows.ctypes.data_as(F), len(h), wave, ctypes.c_double(omega), c.size,
+                                    c.ctypes.data_as(D), out.ctypes.data_as(D))
+            assert np.isfinite(a).all() and np.isfinite(b).all()
+            d = np.abs(a - b)
+            worst[wave] = max(worst[wave], d.max())
+            far = np.abs(b) > 1e-9
+            nsign += int((np.sign(a[far]) != np.sign(b[far])).sum())
+    # values are normalised to max|e| = 1; 30-layer stacks accumulate a few hundred roundings
+    assert worst[1] <= 1e-10 and worst[2] <= 1e-10, worst
+    assert nsign == 0
+
+
 def test_rf_core_equals_oracle(oracle, host_sim):
     from bayhunter_b200 import synthetic
     at = [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 + [D] * 7
