@@ -16,7 +16,11 @@ draws); each step evaluates a different, perturbed batch.
   e2e     the same metric through the host-buffer C-ABI call
           (bh_engine_eval_host): pinned host inputs -> H2D -> kernels -> D2H of
           logL / misfits / status, wall clock, every step
-  roofline / fp64   dominant kernel, timed live with CUDA events inside the engine
+  roofline / fp64   dominant kernel, timed live with CUDA events inside the engine:
+                    algorithmic bytes against the HBM peak, algorithmic flops against
+                    the fp64 DFMA peak (fp64.frac), and the fp64 pipe's utilisation
+                    (fp64.pipe: ncu's figure and executed fp64 warp instructions x 2
+                    cycles against the live launch duration, profiles/traffic.json)
   cpu_baseline      the oracle (reference rfmini C++ when compiled, SURF96 C
                     restatement, numpy likelihood) on the host cores, bounded sample
 
