@@ -29,7 +29,7 @@ enum {
   K_MAGIC = 0,      // 1.5 * 2^52
   K_LOG2E, K_LN2_HI, K_LN2_LO,
   K_Q7, K_Q6, K_Q5, K_Q4, K_Q3, K_Q2, K_Q1,
-  K_TWO_OVER_PI, K_PIO2_1, K_PIO2_2,
+  K_TWO_OVER_PI, K_PIO2_1, K_PIO2_2, K_PIO2_3,
   K_S6, K_S5, K_S4, K_S3, K_S2, K_S1,
   K_C6, K_C5, K_C4, K_C3, K_C2, K_C1,
   K_COUNT
@@ -42,7 +42,7 @@ static __constant__ double kTab[K_COUNT] = {
     // truncation of q9, q8 to their high words and q0 = 0.5).  Coefficients q7 .. q1:
     2.7557268378684192e-06, 2.480152119021773e-05, 1.9841269863105968e-04, 1.3888888917281794e-03,
     8.333333333330051e-03, 4.166666666662399e-02, 1.6666666666666669e-01,
-    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17,   // 2/pi, pi/2 = hi + lo (the next term is -1.5e-33)
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
     1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
     -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
