@@ -941,6 +941,47 @@ BH_HD double search_pending_c(const Search& s) {
   return (s.stage == ST_BR_FIRST || s.stage == ST_BR_STEP) ? s.c1 : s.c3;
 }
 
+// ---- lane dealing ---------------------------------------------------------
+// One round of a warp: `active` = lanes whose chain needs a secular value, `bracket` (a subset) = lanes whose
+// chain walks a bracket and can use more than one.  A refining chain gets one lane; the 32 - popc(active)
+// spare lanes go evenly to the walking chains (quo or quo + 1 more each, at most max_spec lanes per chain).
+// Returns, for `lane`: cnt = lanes of its chain, excl = first lane of its run (the runs are laid out in lane
+// order), total = lanes in use.  Closed form from the two masks -- no scan, no integer division:
+// (extra + 0.5) / nbr stays >= 1/64 away from every integer for 0 <= extra <= 32, 1 <= nbr <= 32, far beyond
+// the error of the approximate fp32 quotient.
+struct LaneDeal { int cnt, excl, total; };
+BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_spec) {
+#if defined(__CUDA_ARCH__)
+#define BH_POPC(x) __popc(x)
+#else
+#define BH_POPC(x) __builtin_popcount(x)
+#endif
+  const int nact = BH_POPC(active), nbr = BH_POPC(bracket);
+  const int extra = 32 - nact;
+#if defined(__CUDA_ARCH__)
+  const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
+#else
+  const int quo = nbr ? (int)(((float)extra + 0.5f) / (float)nbr) : 0;
+#endif
+  const int rem = extra - quo * nbr;
+  const int per = quo + 1;                               // lanes of a walking chain of rank >= rem
+  const bool capped = per >= max_spec;
+  const unsigned below = (1u << lane) - 1u;
+  const int rank = BH_POPC(bracket & below);
+  const unsigned me = 1u << lane;
+  LaneDeal d;
+  d.cnt = 0;
+  if (active & me) {
+    d.cnt = 1;
+    if (bracket & me) { d.cnt = per + (rank < rem ? 1 : 0); if (d.cnt > max_spec) d.cnt = max_spec; }
+  }
+  // walking chains below this lane hold rank * per + min(rank, rem) lanes (or rank * max_spec when capped)
+  d.excl = BH_POPC(active & below) - rank + (capped ? rank * max_spec : rank * per + (rank < rem ? rank : rem));
+  d.total = nact - nbr + (capped ? nbr * max_spec : nbr * per + (nbr < rem ? nbr : rem));
+#undef BH_POPC
+  return d;
+}
+
 // ---- nevill pieces -------------------------------------------------------
 BH_HD void nevill_request_half(Search& s, int next_stage) {
   s.c3 = 0.5 * (s.c1 + s.c2);

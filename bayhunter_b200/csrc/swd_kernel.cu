@@ -209,32 +209,18 @@ swd_kernel(SwdLaunch p) {
     }
     ++rounds;
     unsigned bracket = __ballot_sync(0xffffffffu, want > 1);
-    const int nact = __popc(active), nbr = __popc(bracket);
-    const int extra = 32 - nact;
-    // Lanes per chain: 1 for a chain that refines a root; the spare lanes are dealt evenly to the chains
-    // that walk a bracket (quo or quo + 1 more each, at most max_spec in all).  Counts and their prefix
-    // sums follow in closed form from the two ballots -- no shuffle scan on the round's critical path.
-    //   extra / nbr and extra % nbr for 0 <= extra <= 32, 1 <= nbr <= 32: (extra + 0.5) / nbr stays at least
-    //   1/64 away from every integer, far beyond the error of the approximate fp32 quotient
-    const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
-    const int rem = extra - quo * nbr;
-    const int per = quo + 1;                               // lanes of a walking chain of rank >= rem
-    const bool capped = per >= max_spec;
-    const unsigned below = (1u << lane) - 1u;
-    const int rank = __popc(bracket & below);
-    int cnt = 0;
-    if (want > 0) {
-      cnt = 1;
-      if (want > 1) cnt = min(per + (rank < rem ? 1 : 0), max_spec);
+    // lanes per chain and where each chain's run of lanes starts: closed form from the two ballots
+    // (swd_core.cuh: deal_lanes) -- no shuffle scan, no integer division on the round's critical path
+    const LaneDeal deal = deal_lanes(active, bracket, lane, max_spec);
+    const int cnt = deal.cnt;
+    const unsigned excl = (unsigned)deal.excl, total = (unsigned)deal.total;
+    if (cnt > 0) {
       ws->c[lane] = search_pending_c(s);
       ws->clow[lane] = s.clow;
       ws->omega[lane] = s.omega;
       ws->stage[lane] = s.stage;
       ws->idir[lane] = s.idir;
     }
-    // walking chains below this lane hold rank * per + min(rank, rem) lanes (or rank * max_spec when capped)
-    const unsigned excl = (unsigned)(__popc(active & below) - rank + (capped ? rank * max_spec : rank * per + min(rank, rem)));
-    const unsigned total = (unsigned)(nact - nbr + (capped ? nbr * max_spec : nbr * per + min(nbr, rem)));
     unsigned startmask = __reduce_or_sync(0xffffffffu, cnt > 0 ? (1u << excl) : 0u);
     if (cnt > 0) ws->owner_at[excl] = lane;
     __syncwarp();

@@ -22,6 +22,14 @@ uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 
 extern "C" {
 
+// The kernel's lane dealing for one round (swd_core.cuh: deal_lanes), all 32 lanes.
+void swd_sim_deal(unsigned active, unsigned bracket, int max_spec, int* cnt, int* excl, int* total) {
+  for (int lane = 0; lane < 32; ++lane) {
+    LaneDeal d = deal_lanes(active, bracket, lane, max_spec);
+    cnt[lane] = d.cnt; excl[lane] = d.excl; total[lane] = d.total;
+  }
+}
+
 // Secular values of n trial phase velocities for one model at one period, in the formulation this
 // library was built with (device formulation, or the Fortran's operation order under
 // BH_SECULAR_REFERENCE_ORDER).

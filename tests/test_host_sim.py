@@ -127,6 +127,43 @@ def test_device_formulation_of_secular_functions(oracle, host_sim):
     assert same_count >= 0.98 * total
 
 
+def test_lane_dealing_closed_form(host_sim):
+    """deal_lanes (popcounts of the two ballots) against the sequential definition: one lane per refining
+    chain, the spare lanes dealt evenly to the walking chains in lane order (the first `extra % nbr` of them
+    one more), at most max_spec per chain; runs laid out in lane order without gaps."""
+    rng = np.random.default_rng(5)
+    I32 = ctypes.c_int * 32
+    for trial in range(20000):
+        p0, p1 = rng.random(2)
+        want = np.where(rng.random(32) < p0, 0, np.where(rng.random(32) < p1, 32, 1))
+        if trial < 40:                                    # corner cases: all walking / all refining / one lane
+            want = [np.full(32, 32), np.full(32, 1), np.eye(32, dtype=int)[trial % 32] * 32,
+                    np.eye(32, dtype=int)[trial % 32]][trial % 4]
+        if not want.any():
+            continue
+        max_spec = int(rng.choice([1, 2, 3, 4, 8, 16, 32]))
+        active = int(sum(1 << l for l in range(32) if want[l] > 0))
+        bracket = int(sum(1 << l for l in range(32) if want[l] > 1))
+        nact, nbr = int((want > 0).sum()), int((want > 1).sum())
+        extra = 32 - nact
+        cnt_ref = []
+        for l in range(32):
+            c = 0
+            if want[l] > 0:
+                c = 1
+                if want[l] > 1:
+                    rank = int((want[:l] > 1).sum())
+                    c = min(1 + extra // nbr + (1 if rank < extra % nbr else 0), max_spec)
+            cnt_ref.append(c)
+        excl_ref = np.concatenate(([0], np.cumsum(cnt_ref)[:-1]))
+        cnt, excl, total = I32(), I32(), I32()
+        host_sim.swd_sim_deal(ctypes.c_uint(active), ctypes.c_uint(bracket), max_spec, cnt, excl, total)
+        assert list(cnt) == cnt_ref, (want, max_spec)
+        own = [l for l in range(32) if cnt_ref[l] > 0]
+        assert [excl[l] for l in own] == [int(excl_ref[l]) for l in own]
+        assert set(total) == {sum(cnt_ref)} and sum(cnt_ref) <= 32
+
+
 def test_secular_values_of_the_device_formulation(host_sim, host_sim_reforder):
     """The secular functions as the kernels evaluate them -- records of reciprocals, branch-free half
     terms, Rayleigh layers applied through the rank-one structure of Dunkin's matrix without forming it
