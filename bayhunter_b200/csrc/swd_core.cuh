@@ -251,10 +251,11 @@ BH_HD double secular_rayleigh_reforder(const LayerRow* rows, int stride, int L, 
 #ifndef BH_SWD_WIDE
 #define BH_SWD_WIDE 0
 #endif
-// Love layers whose (vector-independent) terms are formed side by side: 1, 2 or 4
+// 1: the P half of a Rayleigh layer takes its sincos only when some lane of the warp is oscillatory there
 #ifndef BH_P_SINCOS_COND
 #define BH_P_SINCOS_COND 1
 #endif
+// Love layers whose (vector-independent) terms are formed side by side: 1, 2 or 4
 #ifndef BH_LOVE_GROUP
 #define BH_LOVE_GROUP (BH_SWD_WIDE ? 4 : 1)
 #endif
