@@ -125,6 +125,9 @@ struct bh_engine {
   int split_waves = 0;        // 1: Rayleigh and Love curves in separate launches (two streams)
   int rayleigh_sm_pct = 0;    // mixed launch: share of the SMs dedicated to the Rayleigh items (0 = no partition)
   int direct = 0;             // 0 never, 1 when warps are full of chains, 2 always
+  int lockstep = 0;           // swd_lockstep_kernel (every lane owns a chain, pairwise guesses): 0 off, 1 on.  Measured
+                              // equal or slower than swd_kernel on every BASELINE configuration (profiles/r02_swd_restructure.txt)
+  int ls_spw[2] = {0, 0};     // lockstep kernel: models per warp of group / phase curves (0 = rule)
   int concurrent = 1;
   // optional per-kernel timing (bh_engine_set "profile"): event pairs around
   // each launch, recorded on the stream the kernel is launched on
@@ -383,6 +386,13 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "swd_direct")) {
     if (value < 0 || value > 2) return set_err(BH_ERR_ARG, "swd_direct must be 0, 1 or 2");
     e->direct = value;
+  } else if (!strcmp(key, "swd_lockstep")) {
+    if (value < 0 || value > 1) return set_err(BH_ERR_ARG, "swd_lockstep must be 0 or 1");
+    e->lockstep = value;
+  } else if (!strcmp(key, "swd_ls_spw_group") || !strcmp(key, "swd_ls_spw_phase")) {
+    const int g = key[11] == 'g' ? 0 : 1;
+    if (value < 0 || value > (g == 0 ? 16 : 32)) return set_err(BH_ERR_ARG, "models per warp must be 0..32 (<= 16 for group curves)");
+    e->ls_spw[g] = value;
   } else if (!strcmp(key, "concurrent")) {
     e->concurrent = value ? 1 : 0;
 
@@ -653,6 +663,15 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
         bool full = true;
         for (int c = 0; c < sw.ncurves; ++c) full = full && sw.spw[c] == (sw.igr[c] ? 16 : 32);
         sw.direct = (e->direct == 2 || (e->direct == 1 && full)) ? 1 : 0;
+        sw.lockstep = e->lockstep;       // every lane owns a chain (swd_lockstep.cu)
+        if (sw.lockstep) {
+          for (int c = 0; c < sw.ncurves; ++c) {
+            int s_ = e->ls_spw[sw.igr[c] ? 0 : 1];
+            if (s_ <= 0) s_ = sw.igr[c] ? 16 : 32;
+            while (s_ > 1 && (size_t)SWD_REC_FIELDS * lc * s_ * sizeof(double) > 24 * 1024) s_ >>= 1;
+            sw.spw[c] = s_;
+          }
+        }
         sw.queue = nullptr;
         if (pass == 0 && mixed && e->rayleigh_sm_pct > 0 && e->nsm > 1 && e->nsm <= 1024) {
           // dedicate SMs [0, split) to the Rayleigh items, the rest to the Love items
@@ -667,7 +686,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
           BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
         }
         gate_warps += swd_warp_count(sw);
-        if (pass == 0) { KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst); launch_swd(sw, sst); }
+        if (pass == 0) {
+          KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst);
+          if (sw.lockstep) launch_swd_lockstep(sw, sst); else launch_swd(sw, sst);
+        } else if (sw.lockstep) launch_swd_lockstep(sw, sst);
         else launch_swd(sw, sst);
       }
     }

@@ -107,9 +107,12 @@ struct SwdLaunch {
   int type_quota[2];            // CTAs per SM that take the SM's own type before preferring the other
   int type_begin[3];            // filled by launch_swd: first warp of Rayleigh items, Love items, end
   int direct;                   // 1: no speculation (swd_kernel<true>), needs spw = 32 / 16
+  int lockstep;                 // 1: swd_lockstep_kernel (group curves: at most 16 models per warp)
   int* done;                    // += 1 per retired warp (null: not counted)
 };
 void launch_swd(SwdLaunch& p, cudaStream_t st);
+// the same search with every lane owning a chain (swd_lockstep.cu): full batches
+void launch_swd_lockstep(SwdLaunch& p, cudaStream_t st);
 void launch_swd_gate(const int* done, int threshold, cudaStream_t st);
 int swd_warp_count(const SwdLaunch& p);
 size_t swd_smem_bytes(int lcap, int S);

@@ -299,7 +299,7 @@ BH_HD void swd_make_rec(int wave, const LayerRow& r, bool halfspace, double* out
   }
 }
 
-struct HalfTerms { double cs, sn_over_r, r_sn, ex, em; };   // cos-like, sin/r, +-r*sin, exponent, exp(-ex)
+struct HalfTerms { double cs, sn_over_r, r_sn, ex, em, r; };   // cos-like, sin/r, +-r*sin, exponent, exp(-ex), r = sqrt of the (floored) radicand
 
 #define BH_N(...) _Pragma("unroll") for (int i = 0; i < N; ++i) { __VA_ARGS__; }
 
@@ -314,8 +314,20 @@ struct HalfTerms { double cs, sn_over_r, r_sn, ex, em; };   // cos-like, sin/r, 
 // program order.  One warp then keeps the fp64 pipe busy on its own (measured:
 // DFMA latency 8 cycles, issue 2 cycles -> 4 independent chains saturate it),
 // which matters because the searches leave only 1-3 warps per SM sub-partition.
-template <int N>
+// kCond: bit i set = item i takes its sincos only when some lane of the warp is oscillatory there
+// (the P half of a Rayleigh layer: c > vp of that layer is rare) -- a warp-uniform branch.
+template <int N, unsigned kCond = (BH_P_SINCOS_COND && N == 2) ? 1u : 0u>
+BH_HD void half_terms_nk(const double* kk, const double* xk, const double* d, HalfTerms* h);
+template <int N, unsigned kCond = (BH_P_SINCOS_COND && N == 2) ? 1u : 0u>
 BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* h) {
+  double kk[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) kk[i] = k;
+  half_terms_nk<N, kCond>(kk, xk, d, h);
+}
+// the same with a wavenumber per item (two trial velocities side by side)
+template <int N, unsigned kCond>
+BH_HD void half_terms_nk(const double* kk, const double* xk, const double* d, HalfTerms* h) {
 #if defined(__CUDA_ARCH__)
   double s[N], y[N], g[N], hh[N], r[N], p[N], pm[N];
   bool osc[N];
@@ -323,7 +335,7 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   // the oscillatory side gives cos(1e-100 d) = 1, sin(p)/r = d, r sin(p) = 1e-200 d
 #if BH_SWD_LEAN
   // s >= 0: doubles order like their high words; k - xk is exactly +0 or at least one ulp of k
-  BH_N(double dk = k - xk[i]; s[i] = (k + xk[i]) * fabs(dk); osc[i] = __double2hiint(dk) <= 0)
+  BH_N(double dk = kk[i] - xk[i]; s[i] = (kk[i] + xk[i]) * fabs(dk); osc[i] = __double2hiint(dk) <= 0)
   BH_N(s[i] = fm::hi_lo(max(__double2hiint(s[i]), 0x16687e92), __double2loint(s[i])))      // hi word of 1e-200
   BH_N(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i])))
   // halving / doubling of normal numbers: exponent field arithmetic on the high word
@@ -336,8 +348,8 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   BH_N(r[i] = fma(-g[i], hh[i], 1.0))                  // g is final: the residual of g * hh is the error of hh alone
   BH_N(hh[i] = fma(hh[i], r[i], hh[i]))                                    // hh = 1/sqrt(s)
 #else
-  BH_N(s[i] = (k + xk[i]) * fabs(k - xk[i]))
-  BH_N(s[i] = (s[i] < 1.0e-200) ? 1.0e-200 : s[i]; osc[i] = k <= xk[i])
+  BH_N(s[i] = (kk[i] + xk[i]) * fabs(kk[i] - xk[i]))
+  BH_N(s[i] = (s[i] < 1.0e-200) ? 1.0e-200 : s[i]; osc[i] = kk[i] <= xk[i])
   BH_N(asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(s[i])))
   BH_N(g[i] = s[i] * y[i]; hh[i] = 0.5 * y[i])
   BH_N(r[i] = fma(-g[i], hh[i], 0.5))
@@ -351,15 +363,10 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   // exp(-pm) and sincos(p), step by step side by side.  With BH_P_SINCOS_COND the P half of a
   // Rayleigh layer (i = 0 of N = 2) takes its sincos only when some lane of the warp has an
   // oscillatory P term (c > vp of that layer: rare) -- a warp-uniform branch.
-#if BH_P_SINCOS_COND
-  constexpr int I0 = (N == 2) ? 1 : 0;
-#else
-  constexpr int I0 = 0;
-#endif
   double te[N], ts[N], fe[N], ft[N], re[N], rt[N], z[N], pe[N], ps[N], pc[N];
   int ne[N], q[N];
   double sn[N], cn[N];
-#define BH_SC(...) if (i >= I0) { __VA_ARGS__; }
+#define BH_SC(...) if (!((kCond >> i) & 1u)) { __VA_ARGS__; }
   BH_N(te[i] = fma(-pm[i], BH_K(K_LOG2E), BH_K(K_MAGIC)); BH_SC(ts[i] = fma(p[i], BH_K(K_TWO_OVER_PI), BH_K(K_MAGIC))))
   BH_N(ne[i] = __double2loint(te[i]); fe[i] = te[i] - BH_K(K_MAGIC);
        BH_SC(q[i] = __double2loint(ts[i]); ft[i] = ts[i] - BH_K(K_MAGIC)))
@@ -378,16 +385,16 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
   BH_N(pe[i] = fma(pe[i], re[i], 1.0))
 #undef BH_SC
-#if BH_P_SINCOS_COND
-  if (I0 == 1) {
-    q[0] = 0; sn[0] = 0.0; cn[0] = 1.0;
-    if (__any_sync(__activemask(), osc[0])) {
-      double a, c;
-      fm::sincos_cw(p[0], &a, &c);        // the same sequence as above (bh_math.cuh), quadrant already applied
-      sn[0] = a; cn[0] = c;
+  if (kCond != 0u) {
+    bool any = false;
+    BH_N(if ((kCond >> i) & 1u) { q[i] = 0; sn[i] = 0.0; cn[i] = 1.0; any = any || osc[i]; })
+    if (__any_sync(__activemask(), any)) {
+      BH_N(if ((kCond >> i) & 1u) {
+        double a, c;
+        fm::sincos_cw(p[i], &a, &c);      // the same sequence as above (bh_math.cuh), quadrant already applied
+        sn[i] = a; cn[i] = c; })
     }
   }
-#endif
   double em[N], fac[N], ch[N], sh[N];
   BH_N(em[i] = fm::hi_lo(__double2hiint(pe[i]) + (int)((unsigned)ne[i] << 20), __double2loint(pe[i])))
   // quadrant fix-up of sin/cos: swap on bit 0, sign flips as XORs on the high words
@@ -404,13 +411,14 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
 #if BH_SWD_LEAN
   BH_N(h[i].sn_over_r = sh[i] * hh[i]; double rs = g[i] * sh[i];
        h[i].r_sn = fm::hi_lo(__double2hiint(rs) ^ (osc[i] ? (int)0x80000000 : 0), __double2loint(rs));
-       h[i].ex = pm[i]; h[i].em = em[i])
+       h[i].ex = pm[i]; h[i].em = em[i]; h[i].r = g[i])
 #else
   BH_N(h[i].sn_over_r = sh[i] * hh[i]; double rs = g[i] * sh[i]; h[i].r_sn = osc[i] ? -rs : rs;
-       h[i].ex = pm[i]; h[i].em = em[i])
+       h[i].ex = pm[i]; h[i].em = em[i]; h[i].r = g[i])
 #endif
 #else
   for (int i = 0; i < N; ++i) {
+    const double k = kk[i];
     double s = (k + xk[i]) * fabs(k - xk[i]);
     s = (s < 1.0e-200) ? 1.0e-200 : s;
     const bool osc = k <= xk[i];
@@ -428,6 +436,7 @@ BH_HD void half_terms_n(double k, const double* xk, const double* d, HalfTerms* 
     h[i].r_sn = osc ? -rs : rs;
     h[i].ex = pm;
     h[i].em = em;
+    h[i].r = r;
   }
 #endif
 }
@@ -572,21 +581,25 @@ BH_HD DunkinLayer dunkin_from_terms(const double* rec, int fs, const HalfTerms& 
 //     rows (1, 3, 5) -> columns 2, 4:  (cosp y uW - cosq x uX) / rho,    (cosp z uX - cosq w uW) / rho
 // so the product needs three dot products e.u, three scaled sums and two short rows.  Same algebra as
 // dunkin_from_terms + BH_DUNKIN_APPLY, re-associated (values agree to a few ulp of the vector norm).
-BH_HD void dunkin_apply_factored(const double* rec, int fs, const HalfTerms& P, const HalfTerms& S, double k2,
-                                 double iomega2, double& e0, double& e1, double& e2, double& e3, double& e4) {
-  const double rho = rec[RR_RHO * fs], ri = rec[RR_IRHO * fs];
-  const double gk = rec[RR_TB2 * fs] * iomega2;          // gammk = 2 (b/omega)^2
+// a0 = exp(-(pex + sex)) of var (:969-971) from the two half terms
+BH_HD double dunkin_a0(const HalfTerms& P, const HalfTerms& S) {
+  const double exa = P.ex + S.ex;
+#if BH_SWD_LEAN && defined(__CUDA_ARCH__)
+  return (__double2hiint(exa) < 0x404e0000) ? P.em * S.em : 0.0;     // exa >= 0: exa < 60
+#else
+  return (exa < 60.0) ? P.em * S.em : 0.0;
+#endif
+}
+// The vector-independent terms of a layer as they cross from the half-term pass to the propagation pass
+struct DunkinTerms { double cosp, w, x, cosq, y, z, a0; };
+BH_HD void dunkin_apply_terms(double rho, double ri, double gk, const DunkinTerms& t, double k2,
+                              double& e0, double& e1, double& e2, double& e3, double& e4) {
   const double gam = gk * k2;
   const double gm1 = gam - 1.0;
   const double tw = gam + gm1;
-  const double cosp = P.cs, w = P.sn_over_r, x = P.r_sn;
-  const double cosq = S.cs, y = S.sn_over_r, z = S.r_sn;
-  const double exa = P.ex + S.ex;
-#if BH_SWD_LEAN && defined(__CUDA_ARCH__)
-  const double a0 = (__double2hiint(exa) < 0x404e0000) ? P.em * S.em : 0.0;     // exa >= 0: exa < 60
-#else
-  const double a0 = (exa < 60.0) ? P.em * S.em : 0.0;
-#endif
+  const double cosp = t.cosp, w = t.w, x = t.x;
+  const double cosq = t.cosq, y = t.y, z = t.z;
+  const double a0 = t.a0;
   const double cpcq = cosp * cosq, cpy = cosp * y, cpz = cosp * z, cqw = cosq * w, cqx = cosq * x;
   const double A = a0 - cpcq, X = x * z, W = w * y;
   const double f3 = e2 * rho, f5 = e4 * (rho * rho);
@@ -607,6 +620,14 @@ BH_HD void dunkin_apply_factored(const double* rec, int fs, const HalfTerms& P, 
   const double n3 = fma(ri, fma(cpz, dX, -(cqw * dW)), fma(cpcq, e3, -((w * z) * e1)));
   const double sc = fm::pow2_rescale5(n0, n1, n2, n3, n4);
   e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
+}
+BH_HD void dunkin_apply_factored(const double* rec, int fs, const HalfTerms& P, const HalfTerms& S, double k2,
+                                 double iomega2, double& e0, double& e1, double& e2, double& e3, double& e4) {
+  DunkinTerms t;
+  t.cosp = P.cs; t.w = P.sn_over_r; t.x = P.r_sn;
+  t.cosq = S.cs; t.y = S.sn_over_r; t.z = S.r_sn;
+  t.a0 = dunkin_a0(P, S);
+  dunkin_apply_terms(rec[RR_RHO * fs], rec[RR_IRHO * fs], rec[RR_TB2 * fs] * iomega2, t, k2, e0, e1, e2, e3, e4);
 }
 
 // NL consecutive layers l0, l0-1, ... at once: 2*NL half-term chains side by side
@@ -984,6 +1005,11 @@ BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_s
 }
 
 // ---- nevill pieces -------------------------------------------------------
+// x(j) = (-y(j) x(j+1) + y(m+1) x(j)) / (y(m+1) - y(j))  (:651-653), one spelling for every kernel
+BH_HD double neville_step(double yj, double xnext, double ym, double xj, double denom) {
+  return fm::div(fma(-yj, xnext, ym * xj), denom);
+}
+
 BH_HD void nevill_request_half(Search& s, int next_stage) {
   s.c3 = 0.5 * (s.c1 + s.c2);
   s.stage = next_stage;
@@ -1062,7 +1088,7 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
       const double yj = y[j * ts];
       double denom = ym - yj;
       if (fabs(denom) < 1.0e-10 * fabs(ym)) { bad = true; break; }
-      xn = fm::div(-yj * xn + ym * x[j * ts], denom);
+      xn = neville_step(yj, xn, ym, x[j * ts], denom);
       x[j * ts] = xn;
     }
     if (bad) {                                                           // :663-667

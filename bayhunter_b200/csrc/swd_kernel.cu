@@ -172,6 +172,9 @@ swd_kernel(SwdLaunch p) {
 
   unsigned long long consumed = 0, evaluated = 0;
   unsigned rounds = 0;
+#ifdef BH_SWD_TIMING
+  long long cycA = 0, cycB = 0, cycC = 0, lanesB = 0, cycS[3] = {0, 0, 0}, nS[3] = {0, 0, 0};
+#endif
   const int max_spec = p.max_spec;
   const double dc = fabs((double)0.005f);
 
@@ -196,6 +199,9 @@ swd_kernel(SwdLaunch p) {
     evaluated = consumed;
   } else
   for (;;) {
+#ifdef BH_SWD_TIMING
+    long long tA = clock64();
+#endif
     // ---- phase A: owners publish, warp deals lanes ----
     if (role) search_poll_b(s, ctx);
     int want = search_nwant(s, 32);
@@ -225,6 +231,9 @@ swd_kernel(SwdLaunch p) {
     if (cnt > 0) ws->owner_at[excl] = lane;
     __syncwarp();
 
+#ifdef BH_SWD_TIMING
+    long long tB = clock64();
+#endif
     // ---- phase B: every dealt lane evaluates one candidate ----
     if ((unsigned)lane < total) {
       unsigned starts = startmask & (0xffffffffu >> (31 - lane));
@@ -240,10 +249,34 @@ swd_kernel(SwdLaunch p) {
     }
     __syncwarp();
 
+#ifdef BH_SWD_TIMING
+    long long tC = clock64();
+#endif
     // ---- phase C: owners consume their values in reference order ----
+#ifdef BH_SWD_TIMING
+    { const int st0 = s.stage; const long long q0 = clock64();
+      if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx);
+      const long long dq = clock64() - q0;
+      if (cnt > 0) { if (st0 == ST_BR_FIRST) { cycS[0] += dq; nS[0]++; } else if (st0 == ST_BR_STEP) { cycS[1] += dq; nS[1]++; } else { cycS[2] += dq; nS[2]++; } } }
+#else
     if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx);
+#endif
     __syncwarp();
+#ifdef BH_SWD_TIMING
+    long long tD = clock64();
+    cycA += tB - tA; cycB += tC - tB; cycC += tD - tC; lanesB += total;
+#endif
   }
+#ifdef BH_SWD_TIMING
+  for (int q = 0; q < 3; ++q)
+    for (int d = 16; d > 0; d >>= 1) { cycS[q] += __shfl_down_sync(0xffffffffu, cycS[q], d); nS[q] += __shfl_down_sync(0xffffffffu, nS[q], d); }
+  if (lane == 0 && ((gw - p.warp_begin[curve]) % 97) == 5)
+    printf("swd stages curve %d wave %d igr %d: first %lld x %lld  step %lld x %lld  refine %lld x %lld (lane-calls x cycles per call)\n", curve, wave, igr,
+           nS[0], cycS[0] / max(nS[0], 1LL), nS[1], cycS[1] / max(nS[1], 1LL), nS[2], cycS[2] / max(nS[2], 1LL));
+  if (lane == 0 && ((gw - p.warp_begin[curve]) % 97) == 5)
+    printf("swd timing curve %d wave %d igr %d warp %d: rounds %u  A %lld  B %lld  C %lld cycles per round, lanes %.1f\n", curve, wave, igr, gw,
+           rounds, cycA / max(rounds, 1u), cycB / max(rounds, 1u), cycC / max(rounds, 1u), (double)lanesB / max(rounds, 1u));
+#endif
 
   // ---- curve values from the stored roots; validity flag ----
   // role-A lanes write the curve; the second roots of a group curve were stored by
