@@ -210,7 +210,9 @@ class ChainEnsemble(object):
         self.config = make_config(targets, self.priors, self.initparams, seed=seed, max_accepted=max_accepted,
                                   nchains=self.nchains)
         self.nmodels = int(self.config.max_accepted)
-        self.engine = targets.engine(self.nchains, self.maxlayers)
+        # an engine of its own: the device sampler keeps the raw handle, and JointTarget's cached engine is
+        # closed and rebuilt whenever another caller asks for a larger batch or a re-bound law
+        self.engine = targets.new_engine(self.nchains, self.maxlayers)
         h = ctypes.c_void_p()
         _lib.check(self._lib.bh_sampler_create(self.engine._h, ctypes.byref(self.config), self.ntargets,
                                                self.nchains, self.first_chain, ctypes.byref(h)))
@@ -224,6 +226,9 @@ class ChainEnsemble(object):
         if getattr(self, "_h", None):
             self._lib.bh_sampler_destroy(self._h)
             self._h = None
+        if getattr(self, "engine", None) is not None:
+            self.engine.close()
+            self.engine = None
 
     def __del__(self):
         try:
@@ -286,6 +291,11 @@ class ChainEnsemble(object):
         order = ("models", "k", "vpvs", "noise", "logL", "misfits", "propdist", "accepted", "proposed", "iiter",
                  "nstored", "overflow")
         _lib.check(self._lib.bh_sampler_get_state(self._h, *[s[n].ctypes.data for n in order]))
+        # per chain: accepted models that found the chain arrays full, and the iteration of the first one
+        s["overflow_count"] = np.zeros(B, np.int64)
+        s["overflow_iter"] = np.zeros(B, np.int64)
+        _lib.check(self._lib.bh_sampler_get_overflow(self._h, s["overflow_count"].ctypes.data,
+                                                     s["overflow_iter"].ctypes.data))
         return s
 
     def set_state(self, models, k, vpvs, noise, logL=None, misfits=None, propdist=None, accepted=None,
@@ -350,7 +360,7 @@ def save_chain_files(arrays, nstored, chainidx, savepath, maxmodels, final_iter)
     arrays: chain_arrays() of ONE chain (leading axis removed).  Returns the number of main-phase
     rows saved."""
     names = ['models', 'likes', 'misfits', 'noise', 'vpvs']
-    idx1 = weighted_phase(arrays, nstored, 1, 0)
+    idx1 = weighted_phase(arrays, nstored, 1, min(0, final_iter))    # final_iter < 0: a chain that overflowed in burn-in
     idx2 = weighted_phase(arrays, nstored, 2, final_iter)
     if idx2 is None:
         raise ValueError("chain %d accepted no main-phase model" % chainidx)   # reference: AttributeError

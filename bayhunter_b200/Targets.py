@@ -161,11 +161,12 @@ class SingleTarget(object):
         self.valuation.likelihood = (self.valuation.get_likelihood(self.obsdata.y, self.moddata.y, c_inv, logc_det)
                                      if ok else -1e15)
 
-    def to_spec(self):
-        """Engine description of this target (observed data, law, plugin parameters)."""
+    def to_spec(self, generic=False):
+        """Engine description of this target (observed data, law, plugin parameters).  generic: the
+        forward model stays with the plugin object (host side), the engine only evaluates the likelihood."""
         law = self.covariance_law()
         plugin = self.moddata.plugin
-        params = dict(getattr(plugin, "modelparams", {}))
+        params = {} if generic else dict(getattr(plugin, "modelparams", {}))
         params.pop("water", None)
         wtype = params.pop("wtype", None)
         if wtype is not None and {"P": "prf", "SV": "srf"}.get(wtype) != self.ref:
@@ -177,7 +178,7 @@ class SingleTarget(object):
             kw["corr_inv"] = self.valuation.corr_inv
             kw["logcorr_det"] = self.valuation.logcorr_det
         y = self.obsdata.y if self.obsdata.y is not None else np.zeros(self.obsdata.x.size)
-        return TargetSpec(self.ref, self.obsdata.x, y, cov=law, **kw, **params)
+        return TargetSpec(self.ref, self.obsdata.x, y, cov=law, generic=generic, **kw, **params)
 
 
 def _target_class(name, ref, noiseref):
@@ -223,12 +224,25 @@ class JointTarget(object):
         from .surf96_modsw import SurfDisp
         return all(isinstance(t.moddata.plugin, (RFminiModRF, SurfDisp)) for t in self.targets)
 
-    def engine(self, max_batch=1, max_layers=_lib.MAX_LAYERS):
-        """Engine bound to the current laws/parameters (rebuilt when they change)."""
-        specs = [t.to_spec() for t in self.targets]
-        key = (tuple((s.ref, s.cov, s.n, tuple(sorted((k, str(v)) for k, v in s.params.items())),
-                      s.y.tobytes()) for s in specs), max_batch, max_layers)
-        if self._engine is None or self._engine_key[0] != key[0] or \
+    @staticmethod
+    def _spec_key(s):
+        """Everything of a target the device constants are built from: a re-bound law, a new fixed Gauss
+        correlation (R^-1), changed errors or abscissae must all lead to a new engine."""
+        blob = lambda a: None if a is None else np.ascontiguousarray(a).tobytes()
+        return (s.ref, s.generic, s.cov, s.n, tuple(sorted((k, str(v)) for k, v in s.params.items())),
+                s.x.tobytes(), s.y.tobytes(), blob(s.yerr), blob(s.corr_inv), float(s.logcorr_det))
+
+    def new_engine(self, max_batch, max_layers, generic=False):
+        """A fresh Engine for the current laws / parameters, owned by the caller (a ChainEnsemble keeps the
+        raw handle inside its device sampler, so it must not share the cached engine below)."""
+        return Engine([t.to_spec(generic=generic) for t in self.targets], max_batch, max_layers)
+
+    def engine(self, max_batch=1, max_layers=_lib.MAX_LAYERS, generic=False):
+        """Cached engine for evaluate / evaluate_batch, bound to the current laws / parameters; rebuilt when
+        any of them changes or a larger batch / deeper model arrives.  Never handed to a sampler."""
+        specs = [t.to_spec(generic=generic) for t in self.targets]
+        key = tuple(self._spec_key(s) for s in specs)
+        if self._engine is None or self._engine_key != key or \
                 self._engine.max_batch < max_batch or self._engine.max_layers < max_layers:
             if self._engine is not None:
                 self._engine.close()
@@ -238,12 +252,10 @@ class JointTarget(object):
 
     def evaluate(self, h, vp, vs, noise, **kwargs):
         """Single-model evaluation with BayHunter's semantics (src/Targets.py:314-347):
-        leaves `proposallikelihood` (float) and `proposalmisfits` (length T+1)."""
-        if not self._all_native():
-            return self._evaluate_foreign_plugins(h, vp, vs, noise, **kwargs)
-        if any(k in kwargs for k in ("qp", "qs")):
-            raise NotImplementedError("per-layer qp/qs arrays are only supported through "
-                                      "plugin.run_model, not through the fused evaluate")
+        leaves `proposallikelihood` (float) and `proposalmisfits` (length T+1).  Keyword arguments are
+        forwarded to the plugins like the reference does (`rho`; `qp`, `qs` for rfmini)."""
+        if not self._all_native() or any(k != "rho" for k in kwargs):
+            return self._evaluate_through_plugins(h, vp, vs, noise, **kwargs)
         h = np.asarray(h, dtype=np.float64)
         rows = pack_layers(h, vp, vs)[None]
         nlay = np.array([h.size], dtype=np.int32)
@@ -267,14 +279,35 @@ class JointTarget(object):
         self.proposallikelihood = float(logL[0])
         self.proposalmisfits = misfits[0].copy()
 
-    def _evaluate_foreign_plugins(self, h, vp, vs, noise, **kwargs):
-        """A user plugin (templates/myfwd.py contract) is attached to at least one
-        target.  Its forward model is host code this engine cannot run on the
-        device, and this package deliberately has no host likelihood path."""
-        raise NotImplementedError(
-            "JointTarget.evaluate: a non-native forward plugin is attached; bayhunter_b200 only "
-            "evaluates its own SurfDisp / RFminiModRF targets (no CPU likelihood path). Inject "
-            "bayhunter_b200 plugins into the reference's own Targets objects instead.")
+    def _evaluate_through_plugins(self, h, vp, vs, noise, **kwargs):
+        """The reference's own sequence (src/Targets.py:319-347) when the fused device evaluation does not
+        apply: a user plugin (templates/myfwd.py contract) is attached to a target, or keyword arguments
+        other than `rho` must reach the plugins (`qp`, `qs` arrays).  Every target's plugin models its data
+        on the host side of the boundary (this package's plugins on the GPU through the shims, a user
+        plugin wherever it likes); validity, misfits, covariance laws and the joint log-likelihood are
+        evaluated on the device from those synthetics (bh_engine_loglik_host) -- there is no host
+        likelihood path."""
+        rho = kwargs.pop("rho", None)
+        if rho is None:
+            rho = np.asarray(vp) * 0.32 + 0.77           # Berteussen 1977 (src/Targets.py:319)
+        tvalid = np.ones((1, self.ntargets), dtype=np.int32)
+        synth = []
+        for t, target in enumerate(self.targets):
+            target.moddata.calc_synth(h, vp, vs, rho=rho, **kwargs)
+            ok = target._moddata_valid()
+            tvalid[0, t] = 1 if ok else 0
+            synth.append(np.asarray(target.moddata.y, dtype=np.float64) if ok else np.zeros(target.obsdata.y.size))
+        eng = self.engine(1, 2, generic=True)
+        logL, misfits, status = eng.loglik_host(np.concatenate(synth)[None], tvalid,
+                                                np.asarray(noise, dtype=np.float64)[None])
+        if not status[0]:
+            self.proposallikelihood = -1e15
+            self.proposalmisfits = [1e15] * (self.ntargets + 1)
+            return
+        for target, m in zip(self.targets, misfits[0]):
+            target.valuation.misfit = m
+        self.proposallikelihood = float(logL[0])
+        self.proposalmisfits = misfits[0].copy()
 
     def evaluate_batch(self, rows, nlay, noise, rho=None, want_synth=False):
         """Batched evaluation.  Accepts torch CUDA tensors (device path) or numpy

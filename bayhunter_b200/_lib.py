@@ -17,6 +17,7 @@ BH_OK = 0
 BH_ERR_ARG, BH_ERR_CUDA, BH_ERR_UNSUPPORTED, BH_ERR_NO_DEVICE = -1, -2, -3, -4
 
 REF_CODES = {"rdispph": 0, "rdispgr": 1, "ldispph": 2, "ldispgr": 3, "prf": 4, "srf": 5}
+REF_GENERIC = 6     # modelled data supplied by the caller (bh_engine_loglik_host)
 COV_EXP, COV_WHITE, COV_WHITE_SCALED, COV_GAUSS = 0, 1, 2, 3
 MAX_TARGETS, MAX_PERIODS, MAX_LAYERS = 8, 60, 100
 NUM_COUNTERS = 2 + 2 * MAX_TARGETS
@@ -76,6 +77,11 @@ SIGNATURES = {
                        [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5),
     "bh_engine_eval_host": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 4 +
                             [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "bh_engine_eval_host_async": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 4 +
+                                  [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 +
+                                  [ctypes.POINTER(ctypes.c_longlong)]),
+    "bh_engine_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong]),
+    "bh_engine_loglik_host": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3),
     "bh_engine_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "bh_engine_last_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "bh_surfdisp96": (ctypes.c_int, [c_float_p] * 4 + [ctypes.c_int] * 6 +
@@ -87,10 +93,14 @@ SIGNATURES = {
     "bh_sampler_init": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "bh_sampler_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bh_sampler_get_state": (ctypes.c_int, [ctypes.c_void_p] * 13),
+    "bh_sampler_get_overflow": (ctypes.c_int, [ctypes.c_void_p] * 3),
     "bh_sampler_get_chains": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6),
     "bh_sampler_set_state": (ctypes.c_int, [ctypes.c_void_p] * 11),
     "bh_sampler_get_proposal": (ctypes.c_int, [ctypes.c_void_p] * 10),
     "bh_sampler_set_forced_draws": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "surfdisp96_": (None, [c_float_p] * 4 + [c_int_p] * 6 + [c_double_p, c_double_p, c_int_p]),
+    "synrf_cwrap": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 + [c_double_p] * 9),
+    "bh_measure_fp64_peak": (ctypes.c_int, [c_double_p, c_double_p]),
     "bh_synrf": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 +
                  [c_double_p] * 9),
 }

@@ -44,15 +44,26 @@ def build(force=False, verbose=False, extra=()):
     """Compile every CUDA source for sm_100a into one shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libbayhunter_b200.so")
-    if verbose and (res.stdout or res.stderr):
-        print(res.stdout + res.stderr)
+    # several ranks of one torchrun may get here at once: one builds (into a temporary file, renamed into
+    # place when complete), the others wait for the lock and find the library up to date
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        tmp = "%s.%d.tmp" % (LIB, os.getpid())
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            print(" ".join(cmd).replace(tmp, LIB))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed building libbayhunter_b200.so")
+        os.replace(tmp, LIB)
+        if verbose and (res.stdout or res.stderr):
+            print(res.stdout + res.stderr)
     return LIB
 
 

@@ -11,6 +11,7 @@
 // them onto two streams lets the RF warps fill the issue slots the SWD warps
 // leave idle.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -78,6 +79,9 @@ struct bh_engine {
   int curve_off[kMaxTargets] = {0};
   double* rfsynth = nullptr;
   int* tstatus = nullptr;
+  bool has_generic = false;   // a target without a forward model of this library: bh_engine_loglik_host only
+  double* gauss_phi = nullptr;
+  double *gauss_res = nullptr, *gauss_part = nullptr;
   unsigned long long* counters = nullptr;
   int* swd_queue = nullptr;   // work-item counters of the mixed dispersion launch
   int* swd_perm = nullptr;    // [max_batch] models ordered by layer count (ragged batches)
@@ -111,10 +115,27 @@ struct bh_engine {
   double rf_floor = 1e-30;
   int nsm = 0;
   int max_nfreq = 0;
-  // device mirrors for the host-pointer entry point
-  double *d_model = nullptr, *d_noise = nullptr, *d_rho = nullptr, *d_logL = nullptr,
-         *d_misfits = nullptr, *d_synth = nullptr;
-  int *d_nlay = nullptr, *d_status = nullptr;
+  // Host-pointer entry points: two slots of pinned staging + device mirrors, so that the copies of call
+  // k + 1 (stream s_h2d) and of call k (stream s_d2h) run beside the kernels of the call in between.
+  struct HostSlot {
+    double *h_model = nullptr, *h_noise = nullptr, *h_rho = nullptr, *h_logL = nullptr, *h_misfits = nullptr,
+           *h_synth = nullptr;
+    int *h_nlay = nullptr, *h_status = nullptr;
+    double *d_model = nullptr, *d_noise = nullptr, *d_rho = nullptr, *d_logL = nullptr, *d_misfits = nullptr,
+           *d_synth = nullptr;
+    int *d_nlay = nullptr, *d_status = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_kernels = nullptr, ev_done = nullptr;
+    bool busy = false;
+    long long ticket = 0;
+    // delivery of a staged result
+    double *out_logL = nullptr, *out_misfits = nullptr, *out_synth = nullptr;
+    int* out_status = nullptr;
+    int B = 0;
+    bool staged_out = false;
+  } slot[2];
+  bool slots_ready = false;
+  long long next_ticket = 1;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaStream_t s_own = nullptr, s_aux = nullptr, s_aux2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_fork2 = nullptr;
   // tunables
@@ -137,13 +158,17 @@ struct bh_engine {
 };
 
 namespace {
-struct KTimer {   // records start in ctor, stop in dtor when profiling is on
+const char* const kRangeNames[BH_NUM_KERNELS] = {"bh:prepare_swd", "bh:swd", "bh:prepare_rf", "bh:rf_spectrum",
+                                                 "bh:rf_synth", "bh:loglik", "bh:swd_love", "bh:swd_general"};
+struct KTimer {   // an NVTX range around the enqueue of every kernel group; with profiling on also a start / stop event pair
   bh_engine* e; int k; cudaStream_t st;
   KTimer(bh_engine* e_, int k_, cudaStream_t st_) : e(e_), k(k_), st(st_) {
+    nvtxRangePushA(kRangeNames[k]);
     if (e->profile) { cudaEventRecord(e->pev[2 * k], st); e->pev_used[k] = true; }
   }
-  ~KTimer() { if (e->profile) cudaEventRecord(e->pev[2 * k + 1], st); }
+  ~KTimer() { if (e->profile) cudaEventRecord(e->pev[2 * k + 1], st); nvtxRangePop(); }
 };
+struct Range { explicit Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } };
 }  // namespace
 
 static int upload(bh_engine* e, const double* host, size_t n, const double** dev) {
@@ -192,6 +217,17 @@ void bh_engine_destroy(bh_engine* e) {
   if (e->ev_maxn) cudaEventDestroy(e->ev_maxn);
   for (cudaEvent_t ev : e->ev_tune) if (ev) cudaEventDestroy(ev);
   if (e->h_maxn) cudaFreeHost(e->h_maxn);
+  for (auto& sl : e->slot) {
+    void* hp[] = {sl.h_model, sl.h_noise, sl.h_rho, sl.h_logL, sl.h_misfits, sl.h_synth, sl.h_nlay, sl.h_status};
+    for (void* q : hp) if (q) cudaFreeHost(q);
+    void* dp[] = {sl.d_model, sl.d_noise, sl.d_rho, sl.d_logL, sl.d_misfits, sl.d_synth, sl.d_nlay, sl.d_status};
+    for (void* q : dp) if (q) cudaFree(q);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_kernels) cudaEventDestroy(sl.ev_kernels);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+  }
+  if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   if (e->s_own) cudaStreamDestroy(e->s_own);
   if (e->s_aux) cudaStreamDestroy(e->s_aux);
   if (e->s_aux2) cudaStreamDestroy(e->s_aux2);
@@ -220,7 +256,7 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
     TargetDev& d = e->ts.t[t];
     memset(&d, 0, sizeof(d));
     if (s.n < 1 || !s.x || !s.y) { rc = set_err(BH_ERR_ARG, "target needs n >= 1, x and y"); break; }
-    if (!is_swd(s.ref) && !is_rf(s.ref)) { rc = set_err(BH_ERR_ARG, "unknown target ref"); break; }
+    if (!is_swd(s.ref) && !is_rf(s.ref) && s.ref != BH_REF_GENERIC) { rc = set_err(BH_ERR_ARG, "unknown target ref"); break; }
     d.ref = s.ref; d.n = s.n; d.cov = s.cov; d.synth_off = off;
     off += s.n;
     if ((rc = upload(e, s.x, s.n, &d.x)) != BH_OK) break;
@@ -237,7 +273,12 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
       if ((rc = upload(e, se.data(), s.n, &d.serr)) != BH_OK) break;
     } else if (s.cov == BH_COV_GAUSS) {
       if (!s.corr_inv) { rc = set_err(BH_ERR_ARG, "BH_COV_GAUSS needs corr_inv"); break; }
-      if ((rc = upload(e, s.corr_inv, (size_t)s.n * s.n, &d.corr_inv)) != BH_OK) break;
+      // d^T A d = d^T (A + A^T)/2 d: the kernel walks the upper triangle of the symmetric part
+      std::vector<double> sym((size_t)s.n * s.n);
+      for (int i = 0; i < s.n; ++i)
+        for (int j = 0; j < s.n; ++j)
+          sym[(size_t)i * s.n + j] = 0.5 * (s.corr_inv[(size_t)i * s.n + j] + s.corr_inv[(size_t)j * s.n + i]);
+      if ((rc = upload(e, sym.data(), (size_t)s.n * s.n, &d.corr_inv)) != BH_OK) break;
       d.logcorr_det = s.logcorr_det;
     } else if (s.cov != BH_COV_EXP && s.cov != BH_COV_WHITE) {
       rc = set_err(BH_ERR_ARG, "unknown covariance law"); break;
@@ -264,6 +305,8 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
         d.periods = d.x;
       }
       coff += d.kmax;
+    } else if (s.ref == BH_REF_GENERIC) {
+      e->has_generic = true;
     } else {
       // rfmini_modrf.py:41-62: fsamp, tshft, nsamp from the observed time axis
       if (s.n < 2) { rc = set_err(BH_ERR_ARG, "RF target needs >= 2 samples"); break; }
@@ -299,6 +342,14 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
   if (rc == BH_OK) rc = scratch(e, &e->roots, 2 * B * e->curve_stride);
   if (rc == BH_OK) rc = scratch(e, &e->rfsynth, B * (size_t)off);
   if (rc == BH_OK) rc = scratch(e, &e->tstatus, B * kMaxTargets);
+  if (rc == BH_OK) rc = scratch(e, &e->gauss_phi, B * kMaxTargets);
+  {
+    int gn = 0;
+    for (int t = 0; t < ntargets; ++t)
+      if (targets[t].cov == BH_COV_GAUSS && targets[t].n > gn) gn = targets[t].n;
+    if (rc == BH_OK && gn > 0) rc = scratch(e, &e->gauss_res, B * 32 * (size_t)gauss_tile_rows(gn));
+    if (rc == BH_OK && gn > 0) rc = scratch(e, &e->gauss_part, B * (size_t)gauss_tile_rows(gn));
+  }
   if (rc == BH_OK) rc = scratch(e, &e->counters, BH_NUM_COUNTERS);
   if (rc == BH_OK) rc = scratch(e, &e->swd_queue, 2 + 1024);
   if (rc == BH_OK) rc = scratch(e, &e->swd_perm, B);
@@ -312,14 +363,6 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&e->nsm, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (rc == BH_OK) rc = scratch(e, &e->d_model, B * L * 4);
-  if (rc == BH_OK) rc = scratch(e, &e->d_nlay, B);
-  if (rc == BH_OK) rc = scratch(e, &e->d_noise, B * 2 * ntargets);
-  if (rc == BH_OK) rc = scratch(e, &e->d_rho, B * L);
-  if (rc == BH_OK) rc = scratch(e, &e->d_logL, B);
-  if (rc == BH_OK) rc = scratch(e, &e->d_misfits, B * (ntargets + 1));
-  if (rc == BH_OK) rc = scratch(e, &e->d_status, B);
-  if (rc == BH_OK) rc = scratch(e, &e->d_synth, B * (size_t)off);
   if (rc == BH_OK) {
     cudaError_t ce;
     if ((ce = cudaStreamCreateWithFlags(&e->s_own, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -414,6 +457,8 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   if (B < 0 || B > e->max_batch) return set_err(BH_ERR_ARG, "B exceeds max_batch");
   if (lmax < 1 || lmax > e->max_layers) return set_err(BH_ERR_ARG, "lmax exceeds max_layers");
   if (B == 0) return BH_OK;
+  if (e->has_generic)
+    return set_err(BH_ERR_UNSUPPORTED, "a BH_REF_GENERIC target has no forward model here: use bh_engine_loglik_host");
   cudaStream_t st = (cudaStream_t)stream;
   const TargetSet& ts = e->ts;
 
@@ -709,9 +754,23 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       e->maxn_pending = true;
     }
   }
+  LoglikLaunch ll{};
+  ll.ts = ts;
+  ll.curves = e->curves; ll.curve_stride = e->curve_stride;
+  for (int t = 0; t < ts.ntargets; ++t) ll.curve_off[t] = e->curve_off[t];
+  ll.rfsynth = e->rfsynth; ll.tstatus = e->tstatus; ll.noise = noise; ll.B = B;
+  ll.logL = logL; ll.misfits = misfits; ll.status = status; ll.synth = synth; ll.gauss_phi = e->gauss_phi;
+  ll.gauss_res = e->gauss_res; ll.gauss_part = e->gauss_part;
+  // Gauss-law contractions: a single one on a receiver-function target runs right behind its traces on the
+  // RF stream (in the dispersion kernel's shadow); otherwise they share one scratch and run before loglik
+  int ngauss = 0, gauss_t = -1;
+  for (int t = 0; t < ts.ntargets; ++t)
+    if (ts.t[t].cov == BH_COV_GAUSS) { ++ngauss; gauss_t = t; }
+  const bool gauss_on_rf = ngauss == 1 && is_rf(ts.t[gauss_t].ref);
   if (gated && st_rf != st && gate_warps > 0)
     launch_swd_gate(e->swd_done, (int)((long long)gate_warps * e->rf_gate_pct / 100), st_rf);
   launch_rf(st_rf);
+  if (gauss_on_rf) { Range nv("bh:gauss_quadform"); launch_gauss_quadform(ll, gauss_t, st_rf); }
   if (st_rf != st) {
     BH_CUDA(cudaEventRecord(e->ev_join, st_rf));
     BH_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
@@ -727,13 +786,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     KTimer kt(e, BH_K_SWD_GENERAL, st);
     launch_swd_general(gen, st);
   }
-  LoglikLaunch ll{};
-  ll.ts = ts;
-  ll.curves = e->curves; ll.curve_stride = e->curve_stride;
-  for (int t = 0; t < ts.ntargets; ++t) ll.curve_off[t] = e->curve_off[t];
-  ll.rfsynth = e->rfsynth; ll.tstatus = e->tstatus; ll.noise = noise; ll.B = B;
-  ll.logL = logL; ll.misfits = misfits; ll.status = status; ll.synth = synth;
-  { KTimer kt(e, BH_K_LOGLIK, st); launch_loglik(ll, st); }
+  { KTimer kt(e, BH_K_LOGLIK, st);
+    if (!gauss_on_rf)
+      for (int t = 0; t < ts.ntargets; ++t) launch_gauss_quadform(ll, t, st);
+    launch_loglik(ll, st); }
   BH_CUDA(cudaGetLastError());
   return BH_OK;
 }
@@ -750,30 +806,192 @@ int bh_engine_last_kernel_ms(bh_engine* e, float* ms) {
   return BH_OK;
 }
 
-int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay, const double* noise,
-                        const double* rho, int B, int lmax, double* logL, double* misfits,
-                        int* status, double* synth) {
-  if (!e || !model || !nlay || !noise || !logL || !misfits || !status)
+}  // extern "C"
+
+namespace {
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+template <class T>
+int pinned_alloc(T** p, size_t n) {
+  if (*p || n == 0) return BH_OK;
+  BH_CUDA(cudaMallocHost((void**)p, n * sizeof(T)));
+  return BH_OK;
+}
+template <class T>
+int device_alloc_once(T** p, size_t n) {
+  if (*p || n == 0) return BH_OK;
+  BH_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  return BH_OK;
+}
+
+int slots_init(bh_engine* e) {
+  if (e->slots_ready) return BH_OK;
+  BH_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+  BH_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+  const size_t B = (size_t)e->max_batch, L = (size_t)e->max_layers, T = (size_t)e->ts.ntargets;
+  for (auto& sl : e->slot) {
+    int rc;
+    if ((rc = device_alloc_once(&sl.d_model, B * L * 4)) != BH_OK) return rc;
+    if ((rc = device_alloc_once(&sl.d_nlay, B)) != BH_OK) return rc;
+    if ((rc = device_alloc_once(&sl.d_noise, B * 2 * T)) != BH_OK) return rc;
+    if ((rc = device_alloc_once(&sl.d_logL, B)) != BH_OK) return rc;
+    if ((rc = device_alloc_once(&sl.d_misfits, B * (T + 1))) != BH_OK) return rc;
+    if ((rc = device_alloc_once(&sl.d_status, B)) != BH_OK) return rc;
+    BH_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    BH_CUDA(cudaEventCreateWithFlags(&sl.ev_kernels, cudaEventDisableTiming));
+    BH_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+  }
+  e->slots_ready = true;
+  return BH_OK;
+}
+
+// Deliver a finished job: wait for its copies, move staged results to the caller's buffers.
+int slot_finish(bh_engine* e, bh_engine::HostSlot& sl) {
+  if (!sl.busy) return BH_OK;
+  BH_CUDA(cudaEventSynchronize(sl.ev_done));
+  if (sl.staged_out) {
+    const size_t nb = (size_t)sl.B, T = (size_t)e->ts.ntargets;
+    memcpy(sl.out_logL, sl.h_logL, nb * sizeof(double));
+    memcpy(sl.out_misfits, sl.h_misfits, nb * (T + 1) * sizeof(double));
+    memcpy(sl.out_status, sl.h_status, nb * sizeof(int));
+    if (sl.out_synth) memcpy(sl.out_synth, sl.h_synth, nb * e->ts.synth_stride * sizeof(double));
+  }
+  sl.busy = false;
+  return BH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bh_engine_eval_host_async(bh_engine* e, const double* model, const int* nlay, const double* noise,
+                              const double* rho, int B, int lmax, double* logL, double* misfits,
+                              int* status, double* synth, long long* ticket) {
+  if (!e || !model || !nlay || !noise || !logL || !misfits || !status || !ticket)
     return set_err(BH_ERR_ARG, "null argument");
   if (B < 0 || B > e->max_batch) return set_err(BH_ERR_ARG, "B exceeds max_batch");
   if (lmax < 1 || lmax > e->max_layers) return set_err(BH_ERR_ARG, "lmax exceeds max_layers");
+  *ticket = 0;
   if (B == 0) return BH_OK;
-  const int T = e->ts.ntargets;
-  cudaStream_t st = e->s_own;
-  const size_t nb = (size_t)B;
-  BH_CUDA(cudaMemcpyAsync(e->d_model, model, nb * lmax * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-  BH_CUDA(cudaMemcpyAsync(e->d_nlay, nlay, nb * sizeof(int), cudaMemcpyHostToDevice, st));
-  BH_CUDA(cudaMemcpyAsync(e->d_noise, noise, nb * 2 * T * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (rho) BH_CUDA(cudaMemcpyAsync(e->d_rho, rho, nb * lmax * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = bh_engine_eval(e, e->d_model, e->d_nlay, e->d_noise, rho ? e->d_rho : nullptr, B, lmax,
-                          e->d_logL, e->d_misfits, e->d_status, synth ? e->d_synth : nullptr, st);
+  Range nv("bh:eval_host");
+  int rc = slots_init(e);
   if (rc != BH_OK) return rc;
-  BH_CUDA(cudaMemcpyAsync(logL, e->d_logL, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-  BH_CUDA(cudaMemcpyAsync(misfits, e->d_misfits, nb * (T + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-  BH_CUDA(cudaMemcpyAsync(status, e->d_status, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const size_t T = (size_t)e->ts.ntargets, nb = (size_t)B, MB = (size_t)e->max_batch, ML = (size_t)e->max_layers;
+  bh_engine::HostSlot& sl = e->slot[e->next_ticket & 1];
+  if ((rc = slot_finish(e, sl)) != BH_OK) return rc;       // the job that used this slot two calls ago
+  // ---- inputs: straight from pinned caller memory, else through this slot's pinned staging ----
+  const double* src_model = model; const int* src_nlay = nlay; const double* src_noise = noise; const double* src_rho = rho;
+  if (!is_pinned(model)) {
+    if ((rc = pinned_alloc(&sl.h_model, MB * ML * 4)) != BH_OK) return rc;
+    memcpy(sl.h_model, model, nb * lmax * 4 * sizeof(double)); src_model = sl.h_model;
+  }
+  if (!is_pinned(nlay)) {
+    if ((rc = pinned_alloc(&sl.h_nlay, MB)) != BH_OK) return rc;
+    memcpy(sl.h_nlay, nlay, nb * sizeof(int)); src_nlay = sl.h_nlay;
+  }
+  if (!is_pinned(noise)) {
+    if ((rc = pinned_alloc(&sl.h_noise, MB * 2 * T)) != BH_OK) return rc;
+    memcpy(sl.h_noise, noise, nb * 2 * T * sizeof(double)); src_noise = sl.h_noise;
+  }
+  if (rho) {
+    if ((rc = device_alloc_once(&sl.d_rho, MB * ML)) != BH_OK) return rc;
+    if (!is_pinned(rho)) {
+      if ((rc = pinned_alloc(&sl.h_rho, MB * ML)) != BH_OK) return rc;
+      memcpy(sl.h_rho, rho, nb * lmax * sizeof(double)); src_rho = sl.h_rho;
+    }
+  }
+  if (synth && (rc = device_alloc_once(&sl.d_synth, MB * (size_t)e->ts.synth_stride)) != BH_OK) return rc;
+  BH_CUDA(cudaMemcpyAsync(sl.d_model, src_model, nb * lmax * 4 * sizeof(double), cudaMemcpyHostToDevice, e->s_h2d));
+  BH_CUDA(cudaMemcpyAsync(sl.d_nlay, src_nlay, nb * sizeof(int), cudaMemcpyHostToDevice, e->s_h2d));
+  BH_CUDA(cudaMemcpyAsync(sl.d_noise, src_noise, nb * 2 * T * sizeof(double), cudaMemcpyHostToDevice, e->s_h2d));
+  if (rho) BH_CUDA(cudaMemcpyAsync(sl.d_rho, src_rho, nb * lmax * sizeof(double), cudaMemcpyHostToDevice, e->s_h2d));
+  BH_CUDA(cudaEventRecord(sl.ev_in, e->s_h2d));
+  // ---- kernels (the engine's scratch is single: evaluations run one after the other on s_own) ----
+  BH_CUDA(cudaStreamWaitEvent(e->s_own, sl.ev_in, 0));
+  rc = bh_engine_eval(e, sl.d_model, sl.d_nlay, sl.d_noise, rho ? sl.d_rho : nullptr, B, lmax,
+                      sl.d_logL, sl.d_misfits, sl.d_status, synth ? sl.d_synth : nullptr, e->s_own);
+  if (rc != BH_OK) return rc;
+  BH_CUDA(cudaEventRecord(sl.ev_kernels, e->s_own));
+  // ---- results: straight into pinned caller memory, else staged and delivered by bh_engine_wait ----
+  sl.staged_out = !(is_pinned(logL) && is_pinned(misfits) && is_pinned(status) && (!synth || is_pinned(synth)));
+  double *dst_logL = logL, *dst_mis = misfits, *dst_synth = synth;
+  int* dst_stat = status;
+  if (sl.staged_out) {
+    if ((rc = pinned_alloc(&sl.h_logL, MB)) != BH_OK) return rc;
+    if ((rc = pinned_alloc(&sl.h_misfits, MB * (T + 1))) != BH_OK) return rc;
+    if ((rc = pinned_alloc(&sl.h_status, MB)) != BH_OK) return rc;
+    if (synth && (rc = pinned_alloc(&sl.h_synth, MB * (size_t)e->ts.synth_stride)) != BH_OK) return rc;
+    dst_logL = sl.h_logL; dst_mis = sl.h_misfits; dst_stat = sl.h_status; dst_synth = synth ? sl.h_synth : nullptr;
+  }
+  BH_CUDA(cudaStreamWaitEvent(e->s_d2h, sl.ev_kernels, 0));
+  BH_CUDA(cudaMemcpyAsync(dst_logL, sl.d_logL, nb * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+  BH_CUDA(cudaMemcpyAsync(dst_mis, sl.d_misfits, nb * (T + 1) * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+  BH_CUDA(cudaMemcpyAsync(dst_stat, sl.d_status, nb * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
   if (synth)
-    BH_CUDA(cudaMemcpyAsync(synth, e->d_synth, nb * e->ts.synth_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BH_CUDA(cudaMemcpyAsync(dst_synth, sl.d_synth, nb * e->ts.synth_stride * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+  BH_CUDA(cudaEventRecord(sl.ev_done, e->s_d2h));
+  sl.out_logL = logL; sl.out_misfits = misfits; sl.out_status = status; sl.out_synth = synth; sl.B = B;
+  sl.busy = true;
+  sl.ticket = e->next_ticket++;
+  *ticket = sl.ticket;
+  return BH_OK;
+}
+
+int bh_engine_wait(bh_engine* e, long long ticket) {
+  if (!e) return set_err(BH_ERR_ARG, "null engine");
+  if (ticket <= 0) return BH_OK;
+  for (auto& sl : e->slot)
+    if (sl.busy && sl.ticket == ticket) return slot_finish(e, sl);
+  return BH_OK;                // already delivered (its slot was reused, which finishes the older job first)
+}
+
+int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay, const double* noise,
+                        const double* rho, int B, int lmax, double* logL, double* misfits,
+                        int* status, double* synth) {
+  long long ticket = 0;
+  int rc = bh_engine_eval_host_async(e, model, nlay, noise, rho, B, lmax, logL, misfits, status, synth, &ticket);
+  if (rc != BH_OK) return rc;
+  return bh_engine_wait(e, ticket);
+}
+
+int bh_engine_loglik_host(bh_engine* e, const double* synth, const int* tvalid, const double* noise, int B,
+                          double* logL, double* misfits, int* status) {
+  if (!e || !synth || !tvalid || !noise || !logL || !misfits || !status) return set_err(BH_ERR_ARG, "null argument");
+  if (B < 0 || B > e->max_batch) return set_err(BH_ERR_ARG, "B exceeds max_batch");
+  if (B == 0) return BH_OK;
+  int rc = slots_init(e);
+  if (rc != BH_OK) return rc;
+  const TargetSet& ts = e->ts;
+  const size_t T = (size_t)ts.ntargets, nb = (size_t)B, stride = (size_t)ts.synth_stride;
+  bh_engine::HostSlot& sl = e->slot[0];
+  for (auto& s2 : e->slot) if ((rc = slot_finish(e, s2)) != BH_OK) return rc;
+  if ((rc = device_alloc_once(&sl.d_synth, (size_t)e->max_batch * stride)) != BH_OK) return rc;
+  cudaStream_t st = e->s_own;
+  std::vector<int> tv(nb * kMaxTargets, 1);
+  for (size_t b = 0; b < nb; ++b)
+    for (size_t t = 0; t < T; ++t) tv[b * kMaxTargets + t] = tvalid[b * T + t] ? 1 : 0;
+  BH_CUDA(cudaMemcpyAsync(sl.d_synth, synth, nb * stride * sizeof(double), cudaMemcpyHostToDevice, st));
+  BH_CUDA(cudaMemcpyAsync(e->tstatus, tv.data(), tv.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  BH_CUDA(cudaMemcpyAsync(sl.d_noise, noise, nb * 2 * T * sizeof(double), cudaMemcpyHostToDevice, st));
+  LoglikLaunch ll{};
+  ll.ts = ts;
+  ll.curves = e->curves; ll.curve_stride = e->curve_stride;
+  for (int t = 0; t < ts.ntargets; ++t) ll.curve_off[t] = e->curve_off[t];
+  ll.rfsynth = e->rfsynth; ll.given = sl.d_synth; ll.tstatus = e->tstatus; ll.noise = sl.d_noise; ll.B = B;
+  ll.logL = sl.d_logL; ll.misfits = sl.d_misfits; ll.status = sl.d_status; ll.synth = nullptr;
+  ll.gauss_phi = e->gauss_phi; ll.gauss_res = e->gauss_res; ll.gauss_part = e->gauss_part;
+  for (int t = 0; t < ts.ntargets; ++t) launch_gauss_quadform(ll, t, st);
+  launch_loglik(ll, st);
+  BH_CUDA(cudaMemcpyAsync(logL, sl.d_logL, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BH_CUDA(cudaMemcpyAsync(misfits, sl.d_misfits, nb * (T + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BH_CUDA(cudaMemcpyAsync(status, sl.d_status, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
   BH_CUDA(cudaStreamSynchronize(st));
+  BH_CUDA(cudaGetLastError());
   return BH_OK;
 }
 
@@ -924,6 +1142,42 @@ int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a, double 
 }
 
 // ---------------------------------------------------------------------------
+// Link-level drop-in symbols: the raw native entry points of the reference, so that its own glue code
+// (the f2py module generated from surfdisp96.f, the Cython module rfmini.pyx) links against this library
+// instead of surfdisp96.o / librfmini objects without a change.
+// ---------------------------------------------------------------------------
+// subroutine surfdisp96(thkm,vpm,vsm,rhom,nlayer,iflsph,iwave,mode,igr,kmax,t,cg,err)
+// (src/extensions/surfdisp96.f:55-56; real*4 model arrays of NL = 100, double precision t(60), cg(60),
+// integer scalars, err intent(out) :82-86,101): the gfortran symbol, every argument by reference.
+void surfdisp96_(const float* thkm, const float* vpm, const float* vsm, const float* rhom, const int* nlayer,
+                 const int* iflsph, const int* iwave, const int* mode, const int* igr, const int* kmax,
+                 const double* t, double* cg, int* err) {
+  int e = 1;
+  const int rc = bh_surfdisp96(thkm, vpm, vsm, rhom, *nlayer, *iflsph, *iwave, *mode, *igr, *kmax, t, cg, &e);
+  if (rc != BH_OK) {
+    // no error channel besides err: report like "no root found" (the plugin returns (nan, nan)) and say why
+    fprintf(stderr, "surfdisp96_ (libbayhunter_b200): %s\n", bh_last_error());
+    e = 1;
+    for (int k = 0; k < *kmax && k < BH_MAX_PERIODS; ++k) cg[k] = 0.0;
+  }
+  *err = e;
+}
+
+// extern "C" int synrf_cwrap(...) (src/extensions/rfmini/wrap.cpp:26-31, 57-80): always returns 1; fz / fr are
+// the Z / R traces BayHunter discards (zero-filled here).  A failure (no device) has no channel in this
+// prototype: the trace is filled with NaN, which BayHunter rejects (a NaN likelihood fails `u < alpha`).
+int synrf_cwrap(int nsamp, double fsamp, double tshift, double p, double a, double nsv, double sigma, int waveno,
+                int nlay, double* z, double* vp, double* vs, double* rh, double* qp, double* qs, double* fz,
+                double* fr, double* rf) {
+  const int rc = bh_synrf(nsamp, fsamp, tshift, p, a, nsv, sigma, waveno, nlay, z, vp, vs, rh, qp, qs, fz, fr, rf);
+  if (rc != BH_OK) {
+    fprintf(stderr, "synrf_cwrap (libbayhunter_b200): %s\n", bh_last_error());
+    if (rf) for (int i = 0; i < nsamp; ++i) rf[i] = nan("");
+  }
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
 // diagnostics: the straight-line elementary functions of bh_math.cuh, evaluated
 // on the device for a host vector (tests compare them with libm)
 // ---------------------------------------------------------------------------
@@ -945,6 +1199,58 @@ __global__ void debug_math_kernel(const double* __restrict__ x, double* __restri
   out[6 * n + i] = fm::div(1.0, v);
 }
 }  // namespace
+
+namespace {
+// 8 independent DFMA chains per thread: the fp64 pipe's issue rate, not its latency
+__global__ void fp64_peak_kernel(double* out, double a, double b, int iters) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = a + i + threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], b, a);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int bh_measure_fp64_peak(double* tflops, double* sm_mhz_seen) {
+  if (!tflops) return set_err(BH_ERR_ARG, "null argument");
+  if (bh_device_count() < 1) return set_err(BH_ERR_NO_DEVICE, "no CUDA device visible");
+  int dev = 0, nsm = 0, khz = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+  const int threads = 256, blocks = nsm * 4, iters = 4096;
+  double* d = nullptr;
+  BH_CUDA(cudaMalloc((void**)&d, sizeof(double) * threads * blocks));
+  cudaEvent_t e0, e1;
+  BH_CUDA(cudaEventCreate(&e0));
+  BH_CUDA(cudaEventCreate(&e1));
+  fp64_peak_kernel<<<blocks, threads>>>(d, 1.0e-3, 0.999, iters / 8);       // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(d, 1.0e-3, 0.999, iters);
+    cudaEventRecord(e1);
+    cudaError_t ce = cudaEventSynchronize(e1);
+    if (ce != cudaSuccess) { cudaFree(d); return set_err(BH_ERR_CUDA, "fp64 peak probe", ce); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  const double flop = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+  *tflops = flop / (best * 1e-3) / 1e12;
+  if (sm_mhz_seen) *sm_mhz_seen = khz / 1e3;
+  return BH_OK;
+}
 
 extern "C" int bh_debug_math(int n, const double* x, double* out) {
   if (n < 1 || !x || !out) return set_err(BH_ERR_ARG, "bad argument");

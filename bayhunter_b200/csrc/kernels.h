@@ -28,6 +28,20 @@ inline void bh_set_carveout(K kernel) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, bh_carveout_pct());
 }
 
+// Function attributes are per device: a process that drives several GPUs (bh_set_device) must set them on each.
+// One KernelAttrs per kernel instantiation remembers the device it was last configured on.
+struct KernelAttrs { int dev = -1; size_t smem = 0; };
+template <class K>
+inline void bh_configure_kernel(K kernel, size_t dyn_smem, KernelAttrs& a) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (a.dev != dev) { bh_set_carveout(kernel); a.dev = dev; a.smem = 0; }
+  if (dyn_smem > 48 * 1024 && dyn_smem > a.smem) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    a.smem = dyn_smem;
+  }
+}
+
 // ---- per-target device-side description --------------------------------
 struct TargetDev {
   int ref;          // BH_REF_*
@@ -37,7 +51,7 @@ struct TargetDev {
   const double* x;  // [n] device: periods / time axis
   const double* y;  // [n] device: observed
   const double* serr;       // [n] device: yerr / min(yerr) (WHITE_SCALED) or null
-  const double* corr_inv;   // [n*n] device (GAUSS) or null
+  const double* corr_inv;   // [n*n] device (GAUSS): (R^-1 + R^-T) / 2, the part of R^-1 a quadratic form sees; else null
   double logcorr_det;       // slogdet(R) (GAUSS)
   double log_serr_prod;     // log(prod(serr)) (WHITE_SCALED)
   // SWD
@@ -166,6 +180,7 @@ struct LoglikLaunch {
   int curve_stride;
   int curve_off[kMaxTargets];
   const double* rfsynth; // [B][synth_stride] RF traces at synth_off
+  const double* given;   // [B][synth_stride] modelled data of EVERY target supplied by the caller, or null
   const int* tstatus;    // [B][kMaxTargets]
   const double* noise;   // [B][2T]
   int B;
@@ -173,7 +188,12 @@ struct LoglikLaunch {
   double* misfits;       // [B][T+1]
   int* status;           // [B]
   double* synth;         // [B][synth_stride] or null
+  double* gauss_phi;     // [B][kMaxTargets] scratch: d^T R^-1 d of the Gauss-law targets
+  double* gauss_res;     // [B][32 * tile rows] scratch: residuals of the Gauss-law target being contracted
+  double* gauss_part;    // [B][tile rows] scratch: partial sums per tile row
 };
+int gauss_tile_rows(int n);   // 32 x 32 tiles per row / column of R^-1
+void launch_gauss_quadform(const LoglikLaunch& p, int t, cudaStream_t st);   // before launch_loglik, per Gauss-law target
 void launch_loglik(const LoglikLaunch& p, cudaStream_t st);
 
 }  // namespace bh

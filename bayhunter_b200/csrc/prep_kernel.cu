@@ -157,8 +157,8 @@ void launch_prepare(const double* model, const int* nlay, const double* rho, int
   if (total <= 0) return;
   int threads = BH_PREP_THREADS;
   int blocks = (total + threads - 1) / threads;
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(prepare_kernel); carved = true; }
+  static KernelAttrs attrs;
+  bh_configure_kernel(prepare_kernel, 0, attrs);
   prepare_kernel<<<blocks, threads, 0, st>>>(model, nlay, rho, B, lmax, want_swd ? 1 : 0,
                                              want_rf ? 1 : 0, rf_p, rf_nsv, rf_qp, rf_qs, out);
 }
@@ -168,8 +168,8 @@ void launch_prepare_rf_explicit(const double* z, const double* vp, const double*
                                 double p, double nsv, double sigma, PrepOut out, cudaStream_t st) {
   int threads = 128;
   int blocks = (nlay + threads - 1) / threads;
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(prepare_rf_explicit_kernel); carved = true; }
+  static KernelAttrs attrs;
+  bh_configure_kernel(prepare_rf_explicit_kernel, 0, attrs);
   prepare_rf_explicit_kernel<<<blocks, threads, 0, st>>>(z, vp, vs, rho, qp, qs, nlay, p, nsv,
                                                          sigma, out);
 }

@@ -130,8 +130,8 @@ void launch_rf_spectrum(const RfLaunch& p, cudaStream_t st) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = 148LL * 64 * (128 / BH_RF_THREADS);   // grid-stride beyond ~64 CTAs per SM
   if (blocks > cap) blocks = cap;
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(rf_spectrum_kernel); carved = true; }
+  static KernelAttrs attrs;
+  bh_configure_kernel(rf_spectrum_kernel, 0, attrs);
   rf_spectrum_kernel<<<(int)blocks, threads, 0, st>>>(p);
 }
 
@@ -142,13 +142,8 @@ void launch_rf_synth(const RfLaunch& p, cudaStream_t st) {
   if (threads > 512) threads = 512;
   if (threads < 32) threads = 32;
   const size_t smem = sizeof(cd) * ((size_t)N / 2 + (size_t)N / 2 + 1);   // packed samples + twiddles
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(rf_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(rf_synth_kernel); carved = true; }
+  static KernelAttrs attrs;
+  bh_configure_kernel(rf_synth_kernel, smem, attrs);
   rf_synth_kernel<<<p.B, threads, smem, st>>>(p);
 }
 

@@ -42,6 +42,7 @@ struct bh_sampler {
   float *st_models = nullptr, *st_misfits = nullptr, *st_likes = nullptr, *st_noise = nullptr, *st_vpvs = nullptr;
   int* st_iter = nullptr;
   unsigned long long* overflow = nullptr;
+  long long *ovf_count = nullptr, *ovf_iter = nullptr;   // per chain: accepted models that found the arrays full, iteration of the first
   std::vector<void*> owned;
   cudaStream_t st = nullptr;
 };
@@ -61,6 +62,7 @@ struct SamplerDev {      // by-value kernel argument
   float *st_models, *st_misfits, *st_likes, *st_noise, *st_vpvs;
   int* st_iter;
   unsigned long long* overflow;
+  long long *ovf_count, *ovf_iter;
 };
 
 __device__ __forceinline__ Draw chain_draw(const SamplerDev& p, int b, long long iiter) {
@@ -117,7 +119,13 @@ sampler_propose_kernel(SamplerDev p) {
 
 __device__ __forceinline__ void store_row(const SamplerDev& p, int b, long long iiter) {
   const int n = p.nstored[b];
-  if (n >= p.S) { atomicAdd(p.overflow, 1ULL); return; }
+  if (n >= p.S) {
+    // the chain arrays of this chain are full: count, and remember WHEN, so that the dwell time of the last
+    // stored model ends here instead of absorbing every later iteration (save_chain_files)
+    atomicAdd(p.overflow, 1ULL);
+    if (p.ovf_count[b]++ == 0) p.ovf_iter[b] = iiter;
+    return;
+  }
   const int maxl = p.maxl, T = p.T, k = p.cur_k[b];
   const double* cm = p.cur_model + (size_t)b * 2 * maxl;
   float* m = p.st_models + ((size_t)b * p.S + n) * 2 * maxl;
@@ -224,7 +232,7 @@ SamplerDev dev_view(const bh_sampler* s) {
   p.prop_k = s->prop_k; p.prop_valid = s->prop_valid; p.prop_modify = s->prop_modify; p.nlay = s->nlay;
   p.p_status = s->p_status;
   p.st_models = s->st_models; p.st_misfits = s->st_misfits; p.st_likes = s->st_likes; p.st_noise = s->st_noise;
-  p.st_vpvs = s->st_vpvs; p.st_iter = s->st_iter; p.overflow = s->overflow;
+  p.st_vpvs = s->st_vpvs; p.st_iter = s->st_iter; p.overflow = s->overflow; p.ovf_count = s->ovf_count; p.ovf_iter = s->ovf_iter;
   return p;
 }
 
@@ -271,7 +279,7 @@ int bh_sampler_create(bh_engine* e, const bh_sampler_config* c, int ntargets, in
   A(p_logL, B); A(p_misfits, B * (T + 1)); A(forced, B * 4);
   A(prop_k, B); A(prop_valid, B); A(prop_modify, B); A(nlay, B); A(p_status, B);
   A(st_models, B * S * 2 * L); A(st_misfits, B * S * (T + 1)); A(st_likes, B * S); A(st_noise, B * S * 2 * T);
-  A(st_vpvs, B * S); A(st_iter, B * S); A(overflow, 1);
+  A(st_vpvs, B * S); A(st_iter, B * S); A(overflow, 1); A(ovf_count, B); A(ovf_iter, B);
 #undef A
   if (rc == BH_OK && cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess)
     rc = bh_set_error_message(BH_ERR_CUDA, "stream creation");
@@ -287,6 +295,8 @@ int bh_sampler_create(bh_engine* e, const bh_sampler_config* c, int ntargets, in
     cudaMemsetAsync(s->proposed, 0, B * SMP_NPAR * sizeof(long long), s->st);
     cudaMemsetAsync(s->nstored, 0, B * sizeof(int), s->st);
     cudaMemsetAsync(s->overflow, 0, sizeof(unsigned long long), s->st);
+    cudaMemsetAsync(s->ovf_count, 0, B * sizeof(long long), s->st);
+    cudaMemsetAsync(s->ovf_iter, 0, B * sizeof(long long), s->st);
     cudaMemsetAsync(s->cur_model, 0, B * 2 * L * sizeof(double), s->st);
     cudaMemsetAsync(s->prop_model, 0, B * 2 * L * sizeof(double), s->st);
     std::vector<double> pd(B * SMP_NPAR);
@@ -381,6 +391,15 @@ int bh_sampler_get_state(bh_sampler* s, double* models, int* k, double* vpvs, do
   G(overflow, overflow, sizeof(long long));
 #undef G
   SMP_CUDA(cudaStreamSynchronize(st));
+  return BH_OK;
+}
+
+int bh_sampler_get_overflow(bh_sampler* s, long long* count, long long* first_iter) {
+  if (!s) return bh_set_error_message(BH_ERR_ARG, "null sampler");
+  const size_t B = s->B;
+  if (count) SMP_CUDA(cudaMemcpyAsync(count, s->ovf_count, B * sizeof(long long), cudaMemcpyDeviceToHost, s->st));
+  if (first_iter) SMP_CUDA(cudaMemcpyAsync(first_iter, s->ovf_iter, B * sizeof(long long), cudaMemcpyDeviceToHost, s->st));
+  SMP_CUDA(cudaStreamSynchronize(s->st));
   return BH_OK;
 }
 

@@ -1007,7 +1007,11 @@ BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_s
 // ---- nevill pieces -------------------------------------------------------
 // x(j) = (-y(j) x(j+1) + y(m+1) x(j)) / (y(m+1) - y(j))  (:651-653), one spelling for every kernel
 BH_HD double neville_step(double yj, double xnext, double ym, double xj, double denom) {
+#if defined(__CUDA_ARCH__)
   return fm::div(fma(-yj, xnext, ym * xj), denom);
+#else
+  return (-yj * xnext + ym * xj) / denom;      // host simulation: the Fortran's operations, no contraction
+#endif
 }
 
 BH_HD void nevill_request_half(Search& s, int next_stage) {

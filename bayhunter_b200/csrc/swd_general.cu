@@ -47,8 +47,8 @@ void launch_swd_general(const SwdGeneralLaunch& p, cudaStream_t st) {
   if (p.ncurves <= 0 || p.B <= 0) return;
   const int threads = 64;
   const long long total = (long long)p.B * p.ncurves;
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(swd_general_kernel); carved = true; }
+  static KernelAttrs attrs;
+  bh_configure_kernel(swd_general_kernel, 0, attrs);
   swd_general_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(p);
 }
 

@@ -342,13 +342,8 @@ size_t swd_smem_bytes(int lcap, int S) {
 
 template <bool kDirect, int kWave, int kMinBlocks>
 static void launch_inst(const SwdLaunch& p, int warps, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(swd_kernel<kDirect, kWave, kMinBlocks>); carved = true; }
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(swd_kernel<kDirect, kWave, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static KernelAttrs attrs;
+  bh_configure_kernel(swd_kernel<kDirect, kWave, kMinBlocks>, smem, attrs);
   static bool reported = false;
   if (!reported && getenv("BH_DEBUG")) {
     reported = true;

@@ -412,13 +412,8 @@ size_t lockstep_smem_bytes(int lcap, int S, int igr, int kmax) {
 
 template <int kWave, int kMinBlocks>
 void launch_inst(const SwdLaunch& p, int warps, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  static bool carved = false;
-  if (!carved) { bh_set_carveout(swd_lockstep_kernel<kWave, kMinBlocks>); carved = true; }
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(swd_lockstep_kernel<kWave, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static KernelAttrs attrs;
+  bh_configure_kernel(swd_lockstep_kernel<kWave, kMinBlocks>, smem, attrs);
   static bool reported = false;
   if (!reported && getenv("BH_DEBUG")) {
     reported = true;

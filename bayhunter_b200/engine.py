@@ -27,10 +27,12 @@ class TargetSpec(object):
     params   plugin parameters: mode, flsph (SWD); gauss, p, nsv, qp, qs (RF)
     """
 
-    def __init__(self, ref, x, y, cov="exp", yerr=None, corr_inv=None, logcorr_det=0.0, **params):
-        if ref not in _lib.REF_CODES:
+    def __init__(self, ref, x, y, cov="exp", yerr=None, corr_inv=None, logcorr_det=0.0, generic=False, **params):
+        # generic: the forward model is the caller's (a user plugin): likelihood-only engine (Engine.loglik_host)
+        if ref not in _lib.REF_CODES and not generic:
             raise ReferenceError("unknown target ref %r" % (ref,))
         self.ref = ref
+        self.generic = bool(generic)
         self.x = np.ascontiguousarray(x, dtype=np.float64)
         self.y = np.ascontiguousarray(y, dtype=np.float64)
         if self.x.shape != self.y.shape or self.x.ndim != 1:
@@ -48,7 +50,7 @@ class TargetSpec(object):
 
     def to_struct(self):
         s = _lib.BhTarget()
-        s.ref = _lib.REF_CODES[self.ref]
+        s.ref = _lib.REF_GENERIC if self.generic else _lib.REF_CODES[self.ref]
         s.n = self.n
         s.x = self.x.ctypes.data_as(_lib.c_double_p)
         s.y = self.y.ctypes.data_as(_lib.c_double_p)
@@ -56,6 +58,9 @@ class TargetSpec(object):
         s.cov = _COV_NAMES[self.cov]
         s.corr_inv = self.corr_inv.ctypes.data_as(_lib.c_double_p) if self.corr_inv is not None else None
         s.logcorr_det = self.logcorr_det
+        if self.generic:
+            s.mode, s.flsph, s.gauss, s.p, s.nsv, s.qp, s.qs = 1, 0, 1.0, 0.0, -1.0, 0.0, 0.0
+            return s
         s.mode = int(self.params["mode"])
         s.flsph = int(self.params["flsph"])
         s.gauss = float(self.params["gauss"])
@@ -179,6 +184,46 @@ class Engine(object):
             logL.ctypes.data, misfits.ctypes.data, status.ctypes.data,
             synth.ctypes.data if synth is not None else None))
         return logL, misfits, status, synth
+
+    def loglik_host(self, synth, tvalid, noise):
+        """Likelihood of caller-supplied modelled data (bh_engine_loglik_host): synth [B, synth_stride],
+        tvalid [B, T] (0: that target's synthetic was rejected), noise [B, 2T] ->
+        (logL [B], misfits [B, T+1], status [B])."""
+        synth = np.ascontiguousarray(synth, dtype=np.float64)
+        tvalid = np.ascontiguousarray(tvalid, dtype=np.int32)
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        B = synth.shape[0]
+        assert synth.shape == (B, self.synth_stride) and tvalid.shape == (B, self.ntargets)
+        assert noise.size == B * 2 * self.ntargets
+        logL = np.empty(B)
+        misfits = np.empty((B, self.ntargets + 1))
+        status = np.empty(B, dtype=np.int32)
+        _lib.check(self._lib.bh_engine_loglik_host(self._h, synth.ctypes.data, tvalid.ctypes.data, noise.ctypes.data,
+                                                   B, logL.ctypes.data, misfits.ctypes.data, status.ctypes.data))
+        return logL, misfits, status
+
+    def submit_host(self, model, nlay, noise, out, rho=None):
+        """Asynchronous form of eval_host (bh_engine_eval_host_async): enqueues the copies and kernels
+        and returns a ticket at once, so that the caller can prepare and submit the next batch while
+        this one runs (at most two in flight).  `out` = (logL, misfits, status, synth | None) numpy
+        arrays that receive the results when wait(ticket) returns; inputs and outputs must stay alive
+        and untouched until then."""
+        B, L = model.shape[0], model.shape[1]
+        for a, dt in ((model, np.float64), (nlay, np.int32), (noise, np.float64)):
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"]
+        assert model.shape == (B, L, 4) and nlay.shape == (B,) and noise.size == B * 2 * self.ntargets
+        logL, misfits, status, synth = out
+        ticket = ctypes.c_longlong(0)
+        _lib.check(self._lib.bh_engine_eval_host_async(
+            self._h, model.ctypes.data, nlay.ctypes.data, noise.ctypes.data,
+            rho.ctypes.data if rho is not None else None, B, L,
+            logL.ctypes.data, misfits.ctypes.data, status.ctypes.data,
+            synth.ctypes.data if synth is not None else None, ctypes.byref(ticket)))
+        return ticket.value
+
+    def wait(self, ticket):
+        """Block until the outputs of submit_host(ticket) are written."""
+        _lib.check(self._lib.bh_engine_wait(self._h, int(ticket)))
 
     def eval_host_ptr(self, model_ptr, nlay_ptr, noise_ptr, B, L, logL_ptr, misfits_ptr, status_ptr,
                       rho_ptr=None, synth_ptr=None):

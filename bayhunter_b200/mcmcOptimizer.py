@@ -94,9 +94,13 @@ class MCMC_Optimizer(object):
         runtime = time.time() - t0
         logger.info('> All chains terminated after: %.5f s' % runtime)
         st = ens.state()
-        if int(st["overflow"][0]) > 0:
-            logger.warning('%d accepted models did not fit the chain arrays (max_accepted = %d)'
-                           % (int(st["overflow"][0]), self.nmodels))
+        nover = int((st["overflow_count"] > 0).sum())
+        if nover > 0:
+            # the record of such a chain is complete only up to its first unstored model: its files are written
+            # with that iteration as the end of the last stored model's dwell time (weights stay correct)
+            logger.warning('%d chains accepted more models than the chain arrays hold (max_accepted = %d, %d models '
+                           'not stored): their saved posterior ends at the iteration of the first unstored model'
+                           % (nover, self.nmodels, int(st["overflow"][0])))
         maxmodels = float(self.initparams['maxmodels'])
         lo, hi = self.chain_range
         block = 64
@@ -107,8 +111,11 @@ class MCMC_Optimizer(object):
             for j in range(n):
                 one = {k: v[j] for k, v in arr.items()}
                 try:
+                    final_iter = self.iter_phase2
+                    if st["overflow_count"][c0 + j] > 0:
+                        final_iter = min(final_iter, int(st["overflow_iter"][c0 + j]))
                     self.saved[lo + c0 + j] = _sc.save_chain_files(
-                        one, int(st["nstored"][c0 + j]), lo + c0 + j, self.savepath, maxmodels, self.iter_phase2)
+                        one, int(st["nstored"][c0 + j]), lo + c0 + j, self.savepath, maxmodels, final_iter)
                 except ValueError:
                     logger.info('No main phase models accepted.')
         logger.info('### time for inversion: %.2f s' % (time.time() - t0))

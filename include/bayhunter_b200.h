@@ -58,6 +58,8 @@ extern "C" {
 #define BH_REF_LDISPGR 3
 #define BH_REF_PRF 4
 #define BH_REF_SRF 5
+#define BH_REF_GENERIC 6   /* a data set whose forward model is the caller's (templates/myfwd.py plugins,
+                              per-layer Q arrays): only bh_engine_loglik_host evaluates such a target */
 
 /* covariance laws bound per target at chain init (src/SingleChain.py:159-205) */
 #define BH_COV_EXP 0            /* Valuation.get_covariance_exp              */
@@ -161,11 +163,35 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay,
                    double* logL, double* misfits, int* status, double* synth,
                    void* stream);
 
-/* Same with HOST pointers: pinned staging, H2D, kernels, D2H, one stream
- * synchronise before returning. */
+/* Same with HOST pointers (what a ctypes / cgo / JNI binding holding numpy-like arrays calls).
+ * The engine owns two slots of pinned staging buffers and device mirrors: pageable caller memory is
+ * copied into the slot's pinned buffers on the calling thread (pinned caller memory -- cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory -- is used in place), the H2D copies, the kernels and the D2H
+ * copies run on three streams, and results land in pinned memory first.
+ *
+ * bh_engine_eval_host        submit + wait: returns with the outputs written.
+ * bh_engine_eval_host_async  submits and returns a ticket; the copies of this call overlap the
+ *                            kernels of the previous one.  The caller's input AND output buffers must
+ *                            stay valid until bh_engine_wait(ticket) returns; at most two calls are in
+ *                            flight -- a third submit first completes (and delivers) the oldest.
+ * bh_engine_wait             blocks until that call's outputs are in the caller's buffers. */
 int bh_engine_eval_host(bh_engine* e, const double* model, const int* nlay,
                         const double* noise, const double* rho, int B, int lmax,
                         double* logL, double* misfits, int* status, double* synth);
+int bh_engine_eval_host_async(bh_engine* e, const double* model, const int* nlay,
+                              const double* noise, const double* rho, int B, int lmax,
+                              double* logL, double* misfits, int* status, double* synth,
+                              long long* ticket);
+int bh_engine_wait(bh_engine* e, long long ticket);
+
+/* Likelihood only, HOST pointers: the modelled data of every target are the caller's (a forward-model
+ * plugin of its own, src/templates/myfwd.py; or this library's shims called with extra arguments) and the
+ * engine evaluates what JointTarget.evaluate does with them (src/Targets.py:325-347): validity, RMS misfits,
+ * the bound covariance laws, the joint log-likelihood, the sentinels.
+ *   synth  [B][synth_stride] modelled data, targets back to back;  tvalid [B][T] int32: 0 = that target's
+ *   synthetic was rejected (SingleTarget._moddata_valid, src/Targets.py:204-214) -> sentinels for the model. */
+int bh_engine_loglik_host(bh_engine* e, const double* synth, const int* tvalid, const double* noise,
+                          int B, double* logL, double* misfits, int* status);
 
 /* Per-kernel device time of the last eval, measured with CUDA events on the
  * launching streams; needs bh_engine_set(e, "profile", 1) before that eval.
@@ -208,6 +234,23 @@ int bh_synrf(int nsamp, double fsamp, double tshift, double p, double a,
              const double* vp, const double* vs, const double* rh,
              const double* qp, const double* qs, double* fz, double* fr,
              double* rf);
+
+/*
+ * The reference's raw native symbols, for LINKING its own glue unchanged:
+ *   surfdisp96_   gfortran name of `subroutine surfdisp96` (src/extensions/surfdisp96.f:55-56, :82-86,
+ *                 :101): every argument by reference, real*4 thkm/vpm/vsm/rhom(100), double precision
+ *                 t(60), cg(60), integer err out.  What the f2py-generated module calls.
+ *   synrf_cwrap   src/extensions/rfmini/wrap.cpp:26-31, :57-80: same prototype, returns 1.  What
+ *                 rfmini.pyx calls.
+ * Both forward to the shims above; a library error (no device) is reported on stderr and in-band
+ * (err = 1 / NaN trace), as neither prototype has another channel.
+ */
+void surfdisp96_(const float* thkm, const float* vpm, const float* vsm, const float* rhom,
+                 const int* nlayer, const int* iflsph, const int* iwave, const int* mode,
+                 const int* igr, const int* kmax, const double* t, double* cg, int* err);
+int synrf_cwrap(int nsamp, double fsamp, double tshift, double p, double a, double nsv,
+                double sigma, int waveno, int nlay, double* z, double* vp, double* vs,
+                double* rh, double* qp, double* qs, double* fz, double* fr, double* rf);
 
 /* ------------------------------------------------------------------------
  * Lock-step chain ensemble: the sampler around the hot path, on the device.
@@ -273,6 +316,11 @@ int bh_sampler_get_state(bh_sampler* s, double* models, int* k, double* vpvs, do
                          double* logL, double* misfits, double* propdist, long long* accepted,
                          long long* proposed, long long* iiter, int* nstored, long long* overflow);
 
+/* Per chain (HOST, [B] each, either may be NULL): accepted models that did not fit the chain arrays
+ * (max_accepted rows) and the iteration of the first of them.  A chain that overflowed has a complete,
+ * correctly weighted record up to that iteration only. */
+int bh_sampler_get_overflow(bh_sampler* s, long long* count, long long* first_iter);
+
 /* Chain arrays of chains [chain0, chain0 + nchain) to HOST buffers (float32, NaN padded, the
  * layout of the reference's shared arrays): models [n][S][2*(layers_max+1)] (2k values, then
  * NaN), misfits [n][S][T+1], likes [n][S], noise [n][S][2T], vpvs [n][S]; iters [n][S] int32 is
@@ -295,6 +343,11 @@ int bh_sampler_set_forced_draws(bh_sampler* s, const double* draws);
  * the device for n HOST values x; out[7][n] = exp(-|x|), sin x, cos x, 1/x,
  * sqrt|x|, 1/sqrt|x|, 1.0/x (faithful division).  Used by the accuracy tests. */
 int bh_debug_math(int n, const double* x, double* out);
+
+/* Measured fp64 peak of the current device: a kernel of independent DFMA chains on every SM,
+ * best of three, in TFLOP/s (2 flop per DFMA); *sm_mhz_seen (may be NULL) = the device's nominal
+ * clock.  The roofline denominator of bench.py. */
+int bh_measure_fp64_peak(double* tflops, double* sm_mhz_seen);
 
 #ifdef __cplusplus
 }
