@@ -45,8 +45,30 @@ class PosteriorBlock(object):
         self.noise = torch.full((nchains, nsamples, 2 * ntargets), nan, **f)
         self.vpvs = torch.full((nchains, nsamples), nan, **f)
 
+    def record_nuclei(self, s, models, k, vpvs, logL, misfits, noise):
+        """Store sample s of every chain in the reference's own parametrisation: `models` [C, 2*maxlayers]
+        Voronoi nuclei (vs of the k[c] nuclei, then their depths, as bh_sampler_get_state returns them) and
+        the chain's vp/vs.  Rows stored this way are interchangeable with the c_models files: fed through
+        Model.get_vp_vs_h they give back the evaluated model."""
+        import torch
+        C = models.shape[0]
+        maxl = self.models.shape[2] // 2
+        half = models.shape[1] // 2
+        mask = torch.arange(half, device=models.device)[None, :] < k[:, None]
+        nanv = torch.full((C, half), float("nan"), dtype=models.dtype, device=models.device)
+        # chainmodels[n, :model.size] = model: vs then z, contiguous (src/SingleChain.py:501); here fixed halves
+        self.models[:, s, :half] = torch.where(mask, models[:, :half], nanv).to(torch.float32)
+        self.models[:, s, maxl:maxl + half] = torch.where(mask, models[:, half:], nanv).to(torch.float32)
+        self.likes[:, s] = logL.to(torch.float32)
+        self.misfits[:, s] = misfits.to(torch.float32)
+        self.noise[:, s] = noise.to(torch.float32)
+        self.vpvs[:, s] = vpvs.to(torch.float32)
+
     def record(self, s, rows, nlay, logL, misfits, noise):
-        """Store sample s of every chain from the engine's packed rows + outputs."""
+        """Store sample s of every chain from the engine's packed rows + outputs (benchmark / diagnostics).
+        The depth half holds LAYER-CENTRE depths, not Voronoi nuclei (nuclei are not unique given the
+        interfaces), and vpvs is the top row's: such rows describe the evaluated layering but are NOT
+        interchangeable with the reference's c_models files -- use record_nuclei for that."""
         import torch
         C, L, _ = rows.shape
         maxl = self.models.shape[2] // 2

@@ -1037,8 +1037,9 @@ BH_HD void search_root_end(Search& s, const SearchCtx& ctx, double root, bool fo
   } else {
     ctx.rb[s.k] = found ? root : s.cprev;          // :291-293: no second root -> c1 = c(k)
     s.k += 1;
+    // the next period starts at the caller's next search_poll_b: not here, where the first-root lane of the
+    // same warp may be publishing c(k) in this very phase (compute-sanitizer racecheck, profiles/r02_sanitizer.txt)
     s.stage = (s.k >= s.kmax) ? ST_DONE : ST_WAIT;
-    search_poll_b(s, ctx);
   }
 }
 

@@ -81,3 +81,29 @@ def test_outlier_chains_median_rule():
     likes = torch.tensor([[100.0, 101, 99, float("nan")], [100.5, 100, 101, 100], [50.0, 51, 49, 50]])
     idx, dev = chains.outlier_chains(likes, dev=0.05)
     assert idx.tolist() == [2] and float(dev[0]) > 0.4
+
+
+def test_record_nuclei_round_trips_through_the_model_adapter():
+    """Rows stored with record_nuclei are the reference's parametrisation: Model.get_vp_vs_h gives the layering back."""
+    from bayhunter_b200 import Models
+    rng = np.random.default_rng(2)
+    C, maxl, T = 5, 6, 2
+    blk = chains.PosteriorBlock(C, 2, maxl, T)
+    models = np.full((C, 2 * maxl), 0.0)
+    ks = rng.integers(1, maxl + 1, C)
+    for c, k in enumerate(ks):
+        models[c, :k] = np.sort(rng.uniform(2, 5, k))
+        models[c, maxl:maxl + k] = np.sort(rng.uniform(0, 60, k))
+    vpvs = rng.uniform(1.5, 2.0, C)
+    blk.record_nuclei(1, torch.from_numpy(models), torch.from_numpy(ks), torch.from_numpy(vpvs),
+                      torch.zeros(C, dtype=torch.float64), torch.zeros((C, T + 1), dtype=torch.float64),
+                      torch.zeros((C, 2 * T), dtype=torch.float64))
+    for c, k in enumerate(ks):
+        row = blk.models[c, 1].numpy().astype(np.float64)
+        stored = np.concatenate((row[:maxl][:k], row[maxl:][:k]))
+        want = np.concatenate((models[c, :k], models[c, maxl:maxl + k])).astype(np.float32).astype(np.float64)
+        assert np.array_equal(stored, want)
+        assert np.isnan(row[k:maxl]).all() and np.isnan(row[maxl + k:]).all()
+        vp, vs, h = Models.Model.get_vp_vs_h(stored, float(blk.vpvs[c, 1]))
+        vp2, vs2, h2 = Models.Model.get_vp_vs_h(want, float(np.float32(vpvs[c])))
+        assert np.array_equal(h, h2) and np.array_equal(vs, vs2) and np.array_equal(vp, vp2)
