@@ -1,9 +1,10 @@
 """SynthObs with BayHunter's interface (src/SynthObs.py:18-155): synthetic "observed" data
 from the GPU forward plugins, and the reference's correlated-noise generators.
 
-The noise generators are data preparation, not hot path: they are the reference's numpy
-recipes (same module-level RandomState(333), same dense covariance, same
-multivariate_normal call), so a script that seeds nothing gets the reference's noise.
+compute_expnoise / compute_gaussnoise are the reference's numpy recipes (same module-level
+RandomState(333), same dense covariance, same multivariate_normal call), so a script that seeds
+nothing gets the reference's noise; device_noise draws any number of realisations of the same two
+distributions on the GPU (batches of synthetic observations).
 `compute_explike` (a BayWatch display helper) is not provided: this package has no host
 likelihood; evaluate the model through JointTarget.evaluate instead.
 """
@@ -79,6 +80,29 @@ class SynthObs():
         vp = vs * vpvs
         writer = Targets.PReceiverFunction(x=np.arange(10), y=None).moddata.plugin
         writer.write_startmodel(np.array(h), vp, vs, vp * 0.32 + 0.77, 'syn_mod.dat' if outfile is None else outfile)
+
+    @staticmethod
+    def device_noise(law, size, corr=0.85, sigma=0.0125, nreal=1, seed=333):
+        """`nreal` realisations [nreal, size] of the reference's correlated noise drawn on the GPU
+        (bh_correlated_noise): law 'exp' (compute_expnoise) or 'gauss' (compute_gaussnoise).  Same
+        distributions as the numpy recipes below, a different generator (Philox keyed by seed and
+        realisation) -- use the recipes when the reference's RandomState(333) stream itself is wanted."""
+        import ctypes
+        from . import _lib
+        lib = _lib.require_device()
+        out = np.empty((int(nreal), int(size)))
+        factor = None
+        if law == 'gauss':
+            # numpy.random.multivariate_normal: x = z . (sqrt(s)[:, None] * v) with (u, s, v) = svd(cov)
+            _, s, v = np.linalg.svd(corr ** (_lag_matrix(size) ** 2))
+            factor = np.ascontiguousarray(np.sqrt(s)[:, None] * v)
+        elif law != 'exp':
+            raise ValueError("law must be 'exp' or 'gauss'")
+        _lib.check(lib.bh_correlated_noise(_lib.COV_GAUSS if law == 'gauss' else _lib.COV_EXP, int(size), int(nreal),
+                                           float(corr), float(sigma), int(seed),
+                                           None if factor is None else factor.ctypes.data_as(_lib.c_double_p),
+                                           out.ctypes.data_as(_lib.c_double_p)))
+        return out
 
     @staticmethod
     def compute_expnoise(data_obs, corr=0.85, sigma=0.0125):

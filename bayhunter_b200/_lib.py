@@ -100,6 +100,7 @@ SIGNATURES = {
     "bh_sampler_set_forced_draws": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "surfdisp96_": (None, [c_float_p] * 4 + [c_int_p] * 6 + [c_double_p, c_double_p, c_int_p]),
     "synrf_cwrap": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 + [c_double_p] * 9),
+    "bh_correlated_noise": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.c_double] * 2 + [ctypes.c_ulonglong, c_double_p, c_double_p]),
     "bh_measure_fp64_peak": (ctypes.c_int, [c_double_p, c_double_p]),
     "bh_synrf": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int] * 2 +
                  [c_double_p] * 9),

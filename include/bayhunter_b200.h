@@ -339,6 +339,14 @@ int bh_sampler_get_proposal(bh_sampler* s, double* models, int* k, double* vpvs,
                             int* valid, int* modify, double* dvs2, double* logL, double* misfits);
 int bh_sampler_set_forced_draws(bh_sampler* s, const double* draws);
 
+/* Correlated-noise realisations for synthetic observations (src/SynthObs.py:136-155), HOST out [B][n]:
+ * B draws of N(0, sigma^2 R), R_ij = corr^|i-j| (law BH_COV_EXP, compute_expnoise; exact AR(1) recursion) or
+ * R_ij = corr^((i-j)^2) (law BH_COV_GAUSS, compute_gaussnoise; `factor` [n][n] HOST with factor^T factor = R,
+ * computed by the caller like numpy.random.multivariate_normal does: sqrt(s) v of an SVD).  Philox4x32-10
+ * keyed by (seed, realisation): a realisation does not depend on B. */
+int bh_correlated_noise(int law, int n, int B, double corr, double sigma, unsigned long long seed,
+                        const double* factor, double* out);
+
 /* Diagnostics: evaluates the engine's straight-line fp64 elementary functions on
  * the device for n HOST values x; out[7][n] = exp(-|x|), sin x, cos x, 1/x,
  * sqrt|x|, 1/sqrt|x|, 1.0/x (faithful division).  Used by the accuracy tests. */

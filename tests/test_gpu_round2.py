@@ -285,3 +285,30 @@ def test_ensembles_own_their_engines_and_overflow_is_per_chain(oracle):
         if fin >= 0:
             assert total == fin - it[0]          # every iteration up to the first unstored model, no more
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("law,corr", [("exp", 0.85), ("gauss", 0.9), ("exp", 0.0)])
+def test_device_noise_has_the_reference_distribution(law, corr):
+    """bh_correlated_noise against the numpy recipe of SynthObs (src/SynthObs.py:136-155): same covariance
+    (sample covariance of 40 000 draws within sampling error of sigma^2 R), zero mean, reproducible, and a
+    realisation independent of the batch it is drawn in."""
+    from bayhunter_b200.SynthObs import SynthObs, _lag_matrix
+    n, sigma, B = 48, 0.0125, 40000
+    x = SynthObs.device_noise(law, n, corr=corr, sigma=sigma, nreal=B, seed=7)
+    lag = _lag_matrix(n)
+    R = corr ** lag if law == "exp" else corr ** (lag ** 2)
+    if corr == 0.0:
+        R = np.eye(n)
+    C = sigma ** 2 * R
+    S = x.T @ x / B
+    # sampling error of a covariance entry: sqrt((C_ii C_jj + C_ij^2) / B) <= sigma^2 sqrt(2 / B)
+    assert np.abs(S - C).max() <= 6 * sigma ** 2 * np.sqrt(2.0 / B)
+    assert np.abs(x.mean(axis=0)).max() <= 6 * sigma / np.sqrt(B)
+    # the numpy recipe, same size of sample: its deviations from C are of the same size
+    rs = np.random.RandomState(1)
+    y = rs.multivariate_normal(np.zeros(n), C, size=B)
+    assert np.abs(y.T @ y / B - C).max() <= 6 * sigma ** 2 * np.sqrt(2.0 / B)
+    # reproducible and batch independent
+    a = SynthObs.device_noise(law, n, corr=corr, sigma=sigma, nreal=5, seed=7)
+    assert np.array_equal(a, x[:5])
+    assert not np.array_equal(SynthObs.device_noise(law, n, corr=corr, sigma=sigma, nreal=5, seed=8), a)
