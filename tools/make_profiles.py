@@ -24,7 +24,7 @@ for r in rows:
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(P, rnd + "_launch_shares.txt"), "w") as f:
     f.write("# per-kernel totals of profiles/%s_launches.csv (ncu --metrics gpu__time_duration.sum --clock-control none;\n"
-            "# python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sampler-iters 2: 5 evaluations + the e2e pass + a short sampler run).\n"
+            "# python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --sampler-iters 2: 5 evaluations + the sustained run + the e2e passes + a short sampler run).\n"
             "# Times under ncu are cold-cache and serialised: the SHARES are what carries over to the live step.\n" % rnd)
     f.write("%-44s %8s %10s %7s\n" % ("kernel", "launches", "total ms", "share"))
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -38,7 +38,7 @@ for kern, short in (("swd", "swd_kernel"), ("rf", "rf_spectrum")):
     hist = hist[hist.index("warp instructions executed"):] if "warp instructions executed" in hist else ""
     with open(os.path.join(P, "%s_%s_ncu_summary.txt" % (rnd, short if kern == "rf" else "swd_kernel")), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -k regex:%s -s 3 -c 1 python bench.py --steps 1 --warmup 3 "
-                "--no-cpu-baseline --sampler-iters 0  (joint5, B = 8192, one launch after 3 warm-up steps)\n" % short)
+                "--no-cpu-baseline --no-configs --sampler-iters 0  (joint5, B = 8192, one launch after 3 warm-up steps)\n" % short)
         f.write(out)
         f.write("\n## SASS opcode histogram (executed warp instructions)\n" + hist)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
