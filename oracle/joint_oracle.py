@@ -64,6 +64,40 @@ def ref_rfmini():
     return _state["ref"]
 
 
+def ref_surf96():
+    """The reference's own surfdisp96.f (oracle/_ref/libsurf96_ref.so, gfortran symbol surfdisp96_) or None.
+    It exists only where oracle/Makefile found a Fortran compiler next to the reference tree."""
+    if "ref_surf96" not in _state:
+        path = os.path.join(HERE, "_ref", "libsurf96_ref.so")
+        R = None
+        if os.path.exists(path):
+            R = ctypes.CDLL(path)
+            R.surfdisp96_.argtypes = [_F] * 4 + [_I] * 6 + [_D, _D, _I]
+            R.surfdisp96_.restype = None
+        _state["ref_surf96"] = R
+    return _state["ref_surf96"]
+
+
+def surfdisp_fortran(h, vp, vs, rho, ref, periods, mode=1, flsph=0):
+    """The same call as surfdisp() through the compiled reference Fortran (None when it is not built)."""
+    R = ref_surf96()
+    if R is None:
+        return None
+    iwave, igr = SURFTAGS[ref]
+    arrs = [np.zeros(100, dtype=np.float32) for _ in range(4)]
+    for a, v in zip(arrs, (h, vp, vs, rho)):
+        a[:len(v)] = v
+    t = np.zeros(60); t[:len(periods)] = periods
+    cg = np.zeros(60)
+    ints = [ctypes.c_int(v) for v in (len(h), int(flsph), iwave, int(mode), igr, len(periods))]
+    err = ctypes.c_int(0)
+    R.surfdisp96_(*[a.ctypes.data_as(_F) for a in arrs], *[ctypes.byref(i) for i in ints],
+                  t.ctypes.data_as(_D), cg.ctypes.data_as(_D), ctypes.byref(err))
+    if err.value != 0:
+        return np.nan, np.nan
+    return np.asarray(periods, dtype=np.float64), cg[:len(periods)].copy()
+
+
 SURFTAGS = {"rdispgr": (2, 1), "ldispgr": (1, 1), "rdispph": (2, 0), "ldispph": (1, 0)}
 
 
