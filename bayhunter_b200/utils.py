@@ -25,15 +25,43 @@ def _parse_ini(initfile):
     return sections
 
 
+def _literal(text):
+    """Value of an .ini entry: numbers, None / True / False, strings, tuples / lists and arithmetic on numbers
+    ("(2048 * 16)", "1e-5", "2, 5").  The reference hands the text to eval() (src/utils.py:44-56); a parameter file
+    needs none of what that allows beyond this."""
+    import ast
+    import operator as op_
+    ops = {ast.Add: op_.add, ast.Sub: op_.sub, ast.Mult: op_.mul, ast.Div: op_.truediv, ast.Pow: op_.pow,
+           ast.FloorDiv: op_.floordiv, ast.Mod: op_.mod}
+
+    def ev(n):
+        if isinstance(n, ast.Constant) and (n.value is None or isinstance(n.value, (int, float, str, bool))):
+            return n.value
+        if isinstance(n, (ast.Tuple, ast.List)):
+            seq = [ev(e) for e in n.elts]
+            return tuple(seq) if isinstance(n, ast.Tuple) else seq
+        if isinstance(n, ast.UnaryOp) and isinstance(n.op, (ast.USub, ast.UAdd)):
+            v = ev(n.operand)
+            return -v if isinstance(n.op, ast.USub) else +v
+        if isinstance(n, ast.BinOp) and type(n.op) in ops:
+            a, b = ev(n.left), ev(n.right)
+            if not all(isinstance(x, (int, float)) and not isinstance(x, bool) for x in (a, b)):
+                raise ValueError("arithmetic on non-numbers in %r" % text)
+            return ops[type(n.op)](a, b)
+        raise ValueError("unsupported expression in parameter file: %r" % text)
+
+    return ev(ast.parse(text.strip(), mode="eval").body)
+
+
 def _decode(key, val):
     if key in KEYWORDS:
         if len(val) >= 2 and val[0] == val[-1] and val[0] in "'\"":
             return val[1:-1]
         return val
     try:                                    # "(2048 * 16)", "None", "1e-5", "0.9"
-        out = eval(val)
-    except Exception:
-        out = [eval(v) for v in val.split(',') if v.strip()]
+        out = _literal(val)
+    except (SyntaxError, ValueError):
+        out = [_literal(v) for v in val.split(',') if v.strip()]
     if isinstance(out, tuple) and ',' in val and not val.startswith('('):
         out = list(out)                     # configobj hands "a, b" over as a list of strings
     return out
