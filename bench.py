@@ -394,25 +394,25 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the CPU pool forks first, before this process holds a CUDA context, threads or pinned pages; it idles until the end
+    arm = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm()
+
     import torch
     import torch.distributed as dist
     import bayhunter_b200 as bh
     from bayhunter_b200 import synthetic, chains, _lib
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     bh._lib.require_device()
     bh._lib.set_device(local_rank)
-
-    # the CPU pool forks before this process holds many threads and pinned pages; it idles until the end
-    arm = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        arm = CpuArm()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
