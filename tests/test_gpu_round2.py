@@ -312,3 +312,26 @@ def test_device_noise_has_the_reference_distribution(law, corr):
     a = SynthObs.device_noise(law, n, corr=corr, sigma=sigma, nreal=5, seed=7)
     assert np.array_equal(a, x[:5])
     assert not np.array_equal(SynthObs.device_noise(law, n, corr=corr, sigma=sigma, nreal=5, seed=8), a)
+
+
+def test_config4_full_size_properties_and_oracle_sample(oracle):
+    """BASELINE config 4 at one GPU's full share (transd3, B = 4096, 3..31 rows): permutation equivariance and
+    batch-split independence over the whole batch (ragged layer counts are dealt to warps sorted by depth and
+    may run in two launches), and the oracle on a 384-model sample spread over the whole depth range."""
+    eng, specs, otargets, rows, nlay, noise = _engine("transd3", 4096, 80)
+    assert nlay.min() == 3 and nlay.max() == 31
+    base = eng.eval_host(rows, nlay, noise, want_synth=True)
+    perm = np.random.default_rng(5).permutation(4096)
+    out = eng.eval_host(rows[perm], nlay[perm], noise[perm], want_synth=True)
+    for a, b in zip(out, base):
+        assert np.array_equal(a, b[perm], equal_nan=True)
+    part = eng.eval_host(rows[1000:2500], nlay[1000:2500], noise[1000:2500], want_synth=True)
+    for a, b in zip(part, base):
+        assert np.array_equal(a, b[1000:2500], equal_nan=True)
+    sel = np.argsort(nlay, kind="stable")[::11][:384]          # every 11th model by depth: 3 .. 31 rows
+    ref = oracle.evaluate_batch(otargets, np.ascontiguousarray(rows[sel]), np.ascontiguousarray(nlay[sel]),
+                                np.ascontiguousarray(noise[sel]))
+    _compare(tuple(a[sel] for a in base), ref, [(s.ref, s.n) for s in specs])
+    ok = ref[2] == 1
+    e = _logl_check(base[0][sel], ref[0], ok)
+    assert np.median(e) <= 1e-6 and (e <= 1e-6).mean() >= 0.95, (np.median(e), e.max())
