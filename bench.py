@@ -267,15 +267,22 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        # the same workload as the b200 arm; each step evaluates a bounded sample of it
-        "config": {"workload": cfg_description(cfg, args.chains_per_gpu or synthetic.CONFIGS[cfg]["B"], c),
-                   "sample_models_per_step": nev},
+        # the same workload (and the same `config` object) as the b200 arm; each step evaluates a bounded sample of it
+        "config": config_object(cfg, args.chains_per_gpu or synthetic.CONFIGS[cfg]["B"], c, args.gpus),
+        "sample_models_per_step": nev,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
                          "sample": last["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def config_object(cfg, B, c, world):
+    """`config` of the JSON line, identical in both arms."""
+    return {"workload": cfg_description(cfg, B, c), "global_chains": world * B,
+            "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
+            "parallelism": "chains sharded, dp%d" % world}
 
 
 def cfg_description(cfg, B, c, gauss_rf=False):
@@ -651,9 +658,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg_description(cfg, B, c), "global_chains": world * B,
-                       "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
-                       "valid_fraction": valid_frac, "parallelism": "chains sharded, dp%d" % world},
+            "config": config_object(cfg, B, c, world),
+            "valid_fraction": valid_frac,
             "e2e": {"value": rate(e2e_s), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "bh_engine_eval_host_async + bh_engine_wait, two calls in flight, pinned host buffers "
                            "(every step: H2D of its inputs, kernels, D2H of logL / misfits / status)",
