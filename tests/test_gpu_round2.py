@@ -335,3 +335,61 @@ def test_config4_full_size_properties_and_oracle_sample(oracle):
     ok = ref[2] == 1
     e = _logl_check(base[0][sel], ref[0], ok)
     assert np.median(e) <= 1e-6 and (e <= 1e-6).mean() >= 0.95, (np.median(e), e.max())
+
+
+def test_host_entry_edge_cases(oracle):
+    """Empty batches, oversized batches, a likelihood-only call with several models and a Gauss-law target, and the
+    link-level Fortran symbol on the non-default branches (higher mode, earth flattening)."""
+    import bayhunter_b200 as bh
+    from bayhunter_b200 import _lib
+    from bayhunter_b200._lib import BayHunterB200Error
+    eng, specs, otargets, rows, nlay, noise = _engine("swd2", 32, 90)
+    T = eng.ntargets
+    out = (np.empty(0), np.empty((0, T + 1)), np.empty(0, dtype=np.int32), None)
+    t = eng.submit_host(rows[:0], nlay[:0], noise[:0], out)
+    assert t == 0
+    eng.wait(t)
+    big = np.zeros((33, rows.shape[1], 4))
+    with pytest.raises(BayHunterB200Error):
+        eng.eval_host(big, np.zeros(33, np.int32), np.zeros((33, 2 * T)))
+    # likelihood-only entry: three models, exponential + Gauss law, one target rejected in the last model
+    x1, x2 = np.linspace(1, 30, 17), -2.0 + 0.25 * np.arange(70)
+    rng = np.random.default_rng(1)
+    y1, y2 = 3.0 + 0.02 * x1, rng.normal(0, 0.1, 70)
+    ci, ld = bh.gauss_corr_inverse(0.8, 70, rcond=1e-5)
+    gen = bh.Engine([bh.TargetSpec("anything", x1, y1, cov="exp", generic=True),
+                     bh.TargetSpec("prf", x2, y2, cov="gauss", corr_inv=ci, logcorr_det=ld, generic=True)], 4, 2)
+    synth = np.concatenate((y1 + rng.normal(0, 0.02, (3, 17)), y2 + rng.normal(0, 0.05, (3, 70))), axis=1)
+    nz = np.tile([0.3, 0.02, 0.8, 0.05], (3, 1))
+    tv = np.ones((3, 2), dtype=np.int32); tv[2, 1] = 0
+    logL, mis, stat = gen.loglik_host(synth, tv, nz)
+    assert stat.tolist() == [1, 1, 0] and logL[2] == -1e15 and np.all(mis[2] == 1e15)
+    from bayhunter_b200.Targets import Valuation
+    v = Valuation()
+    for b in range(2):
+        c1, d1 = v.get_covariance_exp(0.3, 0.02, 17)
+        want = v.get_likelihood(y1, synth[b, :17], c1, d1) + \
+            v.get_likelihood(y2, synth[b, 17:], ci / 0.05 ** 2, 2 * 70 * np.log(0.05) + ld)
+        assert abs(logL[b] - want) <= 1e-9 * abs(want)
+        assert abs(mis[b, 0] - np.sqrt(np.mean((synth[b, :17] - y1) ** 2))) < 1e-14
+    with pytest.raises(BayHunterB200Error):          # a generic target has no forward model in the engine
+        gen.eval_host(np.zeros((1, 2, 4)), np.array([2], np.int32), nz[:1])
+    # surfdisp96_ on the general branches
+    lib = ctypes.CDLL(_lib.library_path())
+    h = np.array([5., 23., 8., 0.]); vs = np.array([2.7, 3.6, 3.8, 4.4]); vp = vs * 1.73; rho = vp * 0.32 + 0.77
+    periods = np.linspace(2, 20, 12)
+    fp = ctypes.POINTER(ctypes.c_float); dp = ctypes.POINTER(ctypes.c_double)
+    for mode, flsph in ((2, 0), (1, 1)):
+        arr = [np.zeros(100, dtype=np.float32) for _ in range(4)]
+        for a, val in zip(arr, (h, vp, vs, rho)):
+            a[:4] = val
+        tt = np.zeros(60); tt[:12] = periods
+        cg = np.zeros(60)
+        ints = [ctypes.c_int(x) for x in (4, flsph, 2, mode, 0, 12)]
+        err = ctypes.c_int(-1)
+        lib.surfdisp96_.restype = None
+        lib.surfdisp96_(*[a.ctypes.data_as(fp) for a in arr], *[ctypes.byref(i) for i in ints],
+                        tt.ctypes.data_as(dp), cg.ctypes.data_as(dp), ctypes.byref(err))
+        xo, yo = oracle.surfdisp(h, vp, vs, rho, "rdispph", periods, mode=mode, flsph=flsph)
+        assert err.value == 0
+        assert _rel(cg[:12][yo > 0], yo[yo > 0]).max() <= 1e-6
