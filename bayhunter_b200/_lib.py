@@ -21,7 +21,8 @@ REF_GENERIC = 6     # modelled data supplied by the caller (bh_engine_loglik_hos
 COV_EXP, COV_WHITE, COV_WHITE_SCALED, COV_GAUSS = 0, 1, 2, 3
 MAX_TARGETS, MAX_PERIODS, MAX_LAYERS = 8, 60, 100
 NUM_COUNTERS = 2 + 2 * MAX_TARGETS
-KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik", "swd_love", "swd_general")
+KERNEL_NAMES = ("prepare_swd", "swd", "prepare_rf", "rf_spectrum", "rf_synth", "loglik", "swd_love", "swd_general",
+                "swd_pool", "swd_pool_love")
 
 
 class BhTarget(ctypes.Structure):

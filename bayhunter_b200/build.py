@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbayhunter_b200.so")
-SOURCES = ["engine.cu", "prep_kernel.cu", "swd_kernel.cu", "swd_lockstep.cu", "swd_general.cu", "rf_kernel.cu", "loglik_kernel.cu", "sampler.cu", "noise_kernel.cu"]
+SOURCES = ["engine.cu", "prep_kernel.cu", "swd_kernel.cu", "swd_lockstep.cu", "swd_pool.cu", "swd_general.cu", "rf_kernel.cu", "loglik_kernel.cu", "sampler.cu", "noise_kernel.cu"]
 HEADERS = ["bh_common.cuh", "bh_math.cuh", "swd_core.cuh", "swd_eval.cuh", "swd_general_core.cuh", "sampler_core.cuh", "rf_core.cuh", "kernels.h",
            os.path.join("..", "..", "include", "bayhunter_b200.h")]
 

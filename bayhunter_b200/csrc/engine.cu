@@ -148,6 +148,8 @@ struct bh_engine {
   int direct = 0;             // 0 never, 1 when warps are full of chains, 2 always
   int lockstep = 0;           // swd_lockstep_kernel (every lane owns a chain, pairwise guesses): 0 off, 1 on.  Measured
                               // equal or slower than swd_kernel on every BASELINE configuration (profiles/r02_swd_restructure.txt)
+  int pool = -1;              // swd_pool_kernel (a CTA's 128 lanes dealt over the chains of ~28 models): 0 off, 1 on, -1 rule (full batches)
+  int pool_models = 0;        // models per CTA of the pool kernel (0 = rule)
   int ls_spw[2] = {0, 0};     // lockstep kernel: models per warp of group / phase curves (0 = rule)
   int concurrent = 1;
   // optional per-kernel timing (bh_engine_set "profile"): event pairs around
@@ -159,7 +161,8 @@ struct bh_engine {
 
 namespace {
 const char* const kRangeNames[BH_NUM_KERNELS] = {"bh:prepare_swd", "bh:swd", "bh:prepare_rf", "bh:rf_spectrum",
-                                                 "bh:rf_synth", "bh:loglik", "bh:swd_love", "bh:swd_general"};
+                                                 "bh:rf_synth", "bh:loglik", "bh:swd_love", "bh:swd_general",
+                                                 "bh:swd_pool", "bh:swd_pool_love"};
 struct KTimer {   // an NVTX range around the enqueue of every kernel group; with profiling on also a start / stop event pair
   bh_engine* e; int k; cudaStream_t st;
   KTimer(bh_engine* e_, int k_, cudaStream_t st_) : e(e_), k(k_), st(st_) {
@@ -432,6 +435,12 @@ int bh_engine_set(bh_engine* e, const char* key, int value) {
   } else if (!strcmp(key, "swd_lockstep")) {
     if (value < 0 || value > 1) return set_err(BH_ERR_ARG, "swd_lockstep must be 0 or 1");
     e->lockstep = value;
+  } else if (!strcmp(key, "swd_pool")) {
+    if (value < -1 || value > 1) return set_err(BH_ERR_ARG, "swd_pool must be -1 (rule), 0 or 1");
+    e->pool = value;
+  } else if (!strcmp(key, "swd_pool_models")) {
+    if (value < 0 || value > 128) return set_err(BH_ERR_ARG, "swd_pool_models must be in [0, 128]");
+    e->pool_models = value;
   } else if (!strcmp(key, "swd_ls_spw_group") || !strcmp(key, "swd_ls_spw_phase")) {
     const int g = key[11] == 'g' ? 0 : 1;
     if (value < 0 || value > (g == 0 ? 16 : 32)) return set_err(BH_ERR_ARG, "models per warp must be 0..32 (<= 16 for group curves)");
@@ -491,7 +500,24 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     gen.mode[c] = d.mode; gen.flsph[c] = d.flsph;
     gen.periods[c] = d.periods; gen.curve_off[c] = e->curve_off[t];
   }
-  if (!e->split_waves && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
+  // The pool kernel (swd_pool.cu) pays when its CTAs fill the device four to an SM: -4.5 % at 16 k (model, wave type)
+  // pairs, -9 % at 32 k, slower below ~8 k (profiles/r02_swd_restructure.txt section 12).
+  int pool_m = 0;
+  if (e->pool != 0 && nswd > 0) {
+    const int nl = (swl[0].ncurves > 0) + (swl[1].ncurves > 0);
+    bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : (nl == 2 && e->concurrent)) && !e->lockstep;   // rule: Rayleigh and Love CTAs side by side (one wave type alone: 3.09 vs 3.02 ms, swd2 at B = 16384)
+    for (int w = 0; w < 2; ++w) fits = fits && (swl[w].ncurves == 0 || swd_pool_fits(swl[w]));
+    const long long slots = 4LL * e->nsm, pairs = (long long)B * nl;
+    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && pairs * 10 >= slots * 28 * 9 &&
+                                  swd_pool_smem_bytes(lmax, 28) * 4 <= (size_t)220 * 1024))) {
+      pool_m = e->pool_models;
+      if (pool_m <= 0) {
+        pool_m = slots > 0 ? (int)((pairs + slots - 1) / slots) : 28;
+        pool_m = pool_m < 28 ? 28 : (pool_m > 32 ? 32 : pool_m);
+      }
+    }
+  }
+  if (!e->split_waves && pool_m == 0 && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
     // one mixed launch: append the Love curves to the Rayleigh launch
     SwdLaunch& a = swl[0];
     const SwdLaunch& b = swl[1];
@@ -730,12 +756,19 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
           sw.type_quota[1] = (int)((wl + (e->nsm - split) - 1) / (e->nsm - split));
           BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
         }
-        gate_warps += swd_warp_count(sw);
+        const bool pool = pool_m > 0;
+        const int pm = pool ? swd_pool_models(sw, lc, pool_m) : 0;
+        if (pool) sw.queue = nullptr;
+        gate_warps += pool ? swd_pool_warp_count(sw, pm) : swd_warp_count(sw);
+        auto go = [&]() {
+          if (pool) launch_swd_pool(sw, pm, sst);
+          else if (sw.lockstep) launch_swd_lockstep(sw, sst);
+          else launch_swd(sw, sst);
+        };
         if (pass == 0) {
-          KTimer kt(e, w == 0 ? BH_K_SWD : BH_K_SWD_LOVE, sst);
-          if (sw.lockstep) launch_swd_lockstep(sw, sst); else launch_swd(sw, sst);
-        } else if (sw.lockstep) launch_swd_lockstep(sw, sst);
-        else launch_swd(sw, sst);
+          KTimer kt(e, pool ? (w == 0 ? BH_K_SWD_POOL : BH_K_SWD_POOL_LOVE) : (w == 0 ? BH_K_SWD : BH_K_SWD_LOVE), sst);
+          go();
+        } else go();
       }
     }
     if (tuning_now) {

@@ -127,6 +127,12 @@ struct SwdLaunch {
 void launch_swd(SwdLaunch& p, cudaStream_t st);
 // the same search with every lane owning a chain (swd_lockstep.cu): full batches
 void launch_swd_lockstep(SwdLaunch& p, cudaStream_t st);
+// the same search with the 128 lanes of a CTA as one pool over the chains of M models (swd_pool.cu)
+bool swd_pool_fits(const SwdLaunch& p);
+int swd_pool_models(const SwdLaunch& p, int lcap, int want);
+size_t swd_pool_smem_bytes(int lcap, int M);
+int swd_pool_warp_count(const SwdLaunch& p, int M);
+void launch_swd_pool(const SwdLaunch& p, int M, cudaStream_t st);
 void launch_swd_gate(const int* done, int threshold, cudaStream_t st);
 int swd_warp_count(const SwdLaunch& p);
 size_t swd_smem_bytes(int lcap, int S);

@@ -205,7 +205,9 @@ int bh_engine_loglik_host(bh_engine* e, const double* synth, const int* tvalid, 
 #define BH_K_LOGLIK 5
 #define BH_K_SWD_LOVE 6   /* BH_K_SWD is the Rayleigh launch */
 #define BH_K_SWD_GENERAL 7 /* higher modes / flsph = 1 / water-layer models */
-#define BH_NUM_KERNELS 8
+#define BH_K_SWD_POOL 8      /* swd_pool_kernel, Rayleigh launch (full batches; replaces BH_K_SWD) */
+#define BH_K_SWD_POOL_LOVE 9 /* swd_pool_kernel, Love launch, concurrent with the Rayleigh one */
+#define BH_NUM_KERNELS 10
 int bh_engine_last_kernel_ms(bh_engine* e, float* ms);
 
 /* Work counters of the last eval, nsec[BH_NUM_COUNTERS] host ints:

@@ -35,6 +35,25 @@ def test_lockstep_kernel_is_bit_identical(cfg, B):
             assert np.array_equal(a, b, equal_nan=True), (cfg, grp, ph)
 
 
+@pytest.mark.parametrize("cfg,B", [("joint5", 700), ("transd3", 300), ("swd2", 257), ("joint5", 5), ("joint5", 8192)])
+def test_pool_kernel_is_bit_identical(cfg, B):
+    """swd_pool_kernel (a CTA's 128 lanes dealt over the chains of M models) consumes swd_kernel's candidate sequence;
+    at BASELINE's full batch (joint5, 8192 chains) the engine's rule picks it."""
+    eng, specs, _, rows, nlay, noise = _engine(cfg, B, 41)
+    eng.set(swd_pool=0, profile=1)
+    base = eng.eval_host(rows, nlay, noise, want_synth=True)
+    cons0, _ = eng.last_counts()
+    assert "swd" in eng.last_kernel_ms() and "swd_pool" not in eng.last_kernel_ms()
+    for mode, m in ((-1, 0),) if B > 4096 else ((1, 0), (1, 1), (1, 13), (1, 42), (1, 128)):
+        eng.set(swd_pool=mode, swd_pool_models=m)
+        out = eng.eval_host(rows, nlay, noise, want_synth=True)
+        cons, ev = eng.last_counts()
+        assert "swd_pool" in eng.last_kernel_ms(), "the pool kernel did not run"
+        assert cons == cons0 and ev >= cons
+        for a, b in zip(out, base):
+            assert np.array_equal(a, b, equal_nan=True), (cfg, m)
+
+
 def test_async_host_entry_overlaps_and_matches():
     """bh_engine_eval_host_async / bh_engine_wait with pageable numpy buffers, two calls in flight."""
     eng, specs, _, rows, nlay, noise = _engine("joint5", 512, 50)

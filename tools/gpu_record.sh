@@ -12,9 +12,13 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_re
 # every launch of the same command with its device time (cold cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --sampler-iters 2 > gpurun_out/${T}_ncu_bench.log 2>&1
-# the dominant kernels once, full set
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:swd_kernel -s 3 -c 1 -f -o gpurun_out/${T}_swd \
+# the dominant kernels once, full set.  A full joint5 batch runs the dispersion search as two concurrent launches of
+# swd_pool_kernel per evaluation (Rayleigh first, then Love): skip three evaluations, take the fourth one's two launches
+# (ncu serialises them: each capture is that kernel alone on the device)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:swd_pool_kernel -s 6 -c 1 -f -o gpurun_out/${T}_swd \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs --sampler-iters 0 > gpurun_out/${T}_ncu_swd.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:swd_pool_kernel -s 7 -c 1 -f -o gpurun_out/${T}_swdl \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs --sampler-iters 0 > gpurun_out/${T}_ncu_swdl.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rf_spectrum -s 3 -c 1 -f -o gpurun_out/${T}_rf \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs --sampler-iters 0 > gpurun_out/${T}_ncu_rf.log 2>&1
 ls -la gpurun_out | tail -14

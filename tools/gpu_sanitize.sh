@@ -34,8 +34,20 @@ out = (np.empty(40), np.empty((40, 3)), np.empty(40, dtype=np.int32), None)
 t = eng.submit_host(rows, nlay, noise, out); eng.wait(t)
 assert np.array_equal(out[0], a[0])
 print("lockstep + async ok")
+# the pool dispersion kernel: group + phase curve per wave type, Rayleigh and Love launches side by side
+eng2 = bh.Engine([bh.TargetSpec("rdispgr", per, np.full(12, 3.5)), bh.TargetSpec("rdispph", per, np.full(12, 3.5)),
+                  bh.TargetSpec("ldispgr", per, np.full(12, 3.6)), bh.TargetSpec("ldispph", per, np.full(12, 3.6))], 70, 7)
+rows, nlay = synthetic.draw_batch(70, (3, 7), seed=5)
+noise = synthetic.draw_noise(70, ("rdispgr", "rdispph", "ldispgr", "ldispph"), seed=6)
+eng2.set(swd_pool=0)
+a = eng2.eval_host(rows, nlay, noise)
+for m in (0, 9):
+    eng2.set(swd_pool=1, swd_pool_models=m)
+    b = eng2.eval_host(rows, nlay, noise)
+    assert np.array_equal(a[0], b[0])
+print("pool ok")
 PY
 for tool in memcheck racecheck; do
   timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_work.py > gpurun_out/sanitize_$tool.log 2>&1
-  echo "== $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok|sampler ok|lockstep" gpurun_out/sanitize_$tool.log | tail -6
+  echo "== $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok|sampler ok|lockstep|pool ok" gpurun_out/sanitize_$tool.log | tail -6
 done

@@ -31,14 +31,17 @@ with open(os.path.join(P, rnd + "_launch_shares.txt"), "w") as f:
         f.write("%-44s %8d %10.3f %6.1f%%\n" % (k[:44], n, t, 100 * t / tot))
 
 traffic = {}
-for kern, short in (("swd", "swd_kernel"), ("rf", "rf_spectrum")):
+pipes = {}
+for kern, short in (("swd", "swd_pool_kernel_rayleigh"), ("swdl", "swd_pool_kernel_love"), ("rf", "rf_spectrum")):
     rep = os.path.join(G, "%s_%s.ncu-rep" % (tag, kern))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_kernels.py"), rep], capture_output=True, text=True).stdout
     hist = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
     hist = hist[hist.index("warp instructions executed"):] if "warp instructions executed" in hist else ""
-    with open(os.path.join(P, "%s_%s_ncu_summary.txt" % (rnd, short if kern == "rf" else "swd_kernel")), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s -s 3 -c 1 python bench.py --steps 1 --warmup 3 "
-                "--no-cpu-baseline --no-configs --sampler-iters 0  (joint5, B = 8192, one launch after 3 warm-up steps)\n" % short)
+    with open(os.path.join(P, "%s_%s_ncu_summary.txt" % (rnd, short)), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s %s python bench.py --steps 1 --warmup 3 "
+                "--no-cpu-baseline --no-configs --sampler-iters 0  (joint5, B = 8192, one launch after 3 warm-up evaluations%s)\n"
+                % ("rf_spectrum" if kern == "rf" else "swd_pool_kernel", {"swd": "-s 6 -c 1", "swdl": "-s 7 -c 1", "rf": "-s 3 -c 1"}[kern],
+                   "" if kern == "rf" else "; under ncu the kernel has the device to itself, in the live step the Rayleigh and Love launches share the SMs"))
         f.write(out)
         f.write("\n## SASS opcode histogram (executed warp instructions)\n" + hist)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -47,11 +50,13 @@ for kern, short in (("swd", "swd_kernel"), ("rf", "rf_spectrum")):
     for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         i = h.index(key); v = float(vals[i].replace(",", "")); u = units[i].lower()
         tb += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-    traffic[short + ("_kernel" if kern == "rf" else "")] = int(tb)
-    if kern == "swd":
+    traffic[short] = int(tb)
+    if kern != "rf":
         # fp64 pipe: ncu's own utilisation figure and the executed fp64 warp instructions of the launch
         i = h.index("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
         pipe = {"busy_pct_ncu": float(vals[i].replace(",", ""))}
+        i = h.index("gpu__time_duration.sum"); v = float(vals[i].replace(",", "")); u = units[i].lower()
+        pipe["ms_ncu"] = v / 1e6 if u.startswith("n") else (v / 1e3 if u.startswith("u") else v)
         tot = 0; share = 0.0
         for line in hist.splitlines():
             t = line.split()
@@ -59,10 +64,20 @@ for kern, short in (("swd", "swd_kernel"), ("rf", "rf_spectrum")):
             elif len(t) >= 2 and t[0] in ("DFMA", "DMUL", "DADD", "DSETP"): share += float(t[1].rstrip("%"))
         pipe["fp64_warp_instructions"] = int(tot * share / 100.0)
         pipe["warp_instructions"] = tot
+        pipes[short] = pipe
+tsum = sum(p["ms_ncu"] for p in pipes.values())
+pair = {"kernel": "swd_pool",
+        "busy_pct_ncu": sum(p["busy_pct_ncu"] * p["ms_ncu"] for p in pipes.values()) / tsum,
+        "fp64_warp_instructions": sum(p["fp64_warp_instructions"] for p in pipes.values()),
+        "warp_instructions": sum(p["warp_instructions"] for p in pipes.values()),
+        "launches": pipes}
 tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in this directory (bytes)",
-      "joint5": {"swd_kernel": traffic["swd_kernel"], "rf_spectrum_kernel": traffic["rf_spectrum_kernel"]},
-      "fp64_pipe": {"_comment": "swd_kernel, same capture: sm__pipe_fp64_cycles_active (% of peak) and executed DFMA+DMUL+DADD+DSETP warp "
-                                "instructions per launch (each occupies the pipe of its sub-partition for 2 cycles)",
-                    "joint5": pipe}}
+      "joint5": {"swd_pool_kernel": traffic["swd_pool_kernel_rayleigh"] + traffic["swd_pool_kernel_love"],
+                 "swd_pool_kernel_rayleigh": traffic["swd_pool_kernel_rayleigh"], "swd_pool_kernel_love": traffic["swd_pool_kernel_love"],
+                 "rf_spectrum_kernel": traffic["rf_spectrum"]},
+      "fp64_pipe": {"_comment": "the two swd_pool_kernel launches of one evaluation (Rayleigh, Love), each captured alone: "
+                                "sm__pipe_fp64_cycles_active (% of peak; pair = time-weighted) and executed DFMA+DMUL+DADD+DSETP warp "
+                                "instructions (each occupies the pipe of its sub-partition for 2 cycles)",
+                    "joint5": pair}}
 json.dump(tj, open(os.path.join(P, "traffic.json"), "w"), indent=2)
 print(open(os.path.join(P, rnd + "_launch_shares.txt")).read()); print(tj)
