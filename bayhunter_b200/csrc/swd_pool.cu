@@ -129,6 +129,13 @@ swd_pool_kernel(SwdLaunch p, int M) {
 
   // (A variant with three barriers per round -- the next round's ballots taken at the end of the consume step -- was
   //  slower: 3.51 vs 3.45 ms, 128 vs 125 registers.)
+#ifdef BH_SWD_TIMING
+  long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define BH_TICK(i) { const long long now_ = clock64(); cyc[i] += now_ - tick_; tick_ = now_; }
+  long long tick_ = clock64();
+#else
+#define BH_TICK(i)
+#endif
   for (;;) {
     // ---- phase A: owners say what they want, the CTA deals its lanes ----
     if (role) search_poll_b(s, ctx);
@@ -136,7 +143,9 @@ swd_pool_kernel(SwdLaunch p, int M) {
     const unsigned a_w = __ballot_sync(0xffffffffu, want > 0), b_w = __ballot_sync(0xffffffffu, want > 1);
     if (lane == 0) { ws->act[warp] = a_w; ws->brk[warp] = b_w; }
     if (s.stage == ST_WAIT) ws->any_wait = 1;      // a second-root chain whose first root may arrive this round
+    BH_TICK(0)
     __syncthreads();
+    BH_TICK(1)
     int nact = 0, nbr = 0, act_below = 0, rank = 0;
 #pragma unroll
     for (int w = 0; w < kPoolWarps; ++w) {
@@ -177,7 +186,9 @@ swd_pool_kernel(SwdLaunch p, int M) {
       ws->owner_at[excl] = t;
       atomicOr(&ws->startbits[excl >> 5], 1u << (excl & 31));
     }
+    BH_TICK(2)
     __syncthreads();
+    BH_TICK(3)
 
     // ---- phase B: every dealt lane evaluates one candidate ----
     if (t < total) {
@@ -192,14 +203,24 @@ swd_pool_kernel(SwdLaunch p, int M) {
       ws->del[t] = secular_rec(wave, rec + ws->col[own], fs, M, ws->nlay[own], fm::div(omega, c), omega);
       evaluated += 1;
     }
+    BH_TICK(4)
     __syncthreads();
+    BH_TICK(5)
 
     // ---- phase C: owners consume their values in reference order ----
     if (t < kPoolWarps) ws->startbits[t] = 0u;
     if (t == 0) ws->any_wait = 0;
     if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx);
+    BH_TICK(6)
     __syncthreads();
+    BH_TICK(7)
   }
+#ifdef BH_SWD_TIMING
+  if (lane == 0 && (blockIdx.x % 59) == 7)
+    printf("pool wave %d cta %d warp %d rounds %u: poll+ballot %lld | wait %lld | deal+publish %lld | wait %lld | evaluate %lld | wait %lld | consume %lld | wait %lld cycles per round\n",
+           wave, (int)blockIdx.x, warp, rounds, cyc[0] / max(rounds, 1u), cyc[1] / max(rounds, 1u), cyc[2] / max(rounds, 1u), cyc[3] / max(rounds, 1u),
+           cyc[4] / max(rounds, 1u), cyc[5] / max(rounds, 1u), cyc[6] / max(rounds, 1u), cyc[7] / max(rounds, 1u));
+#endif
 
   // ---- curve values from the stored roots; validity flag ----
   __shared__ int done_flag[kPoolLanes];
