@@ -954,8 +954,22 @@ BH_HD int search_nwant(const Search& s, int nmax) {
 
 // i-th pending candidate (i = 0 is the one the reference evaluates next).
 // The published (stage, c, idir, clow) tuple is all a worker lane needs.
-BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i) {
-  if (stage > ST_BR_STEP) return c;      // c3 (refine)
+// A refining chain (stage > ST_BR_STEP) publishes c = c3, clow = c1 and c2: candidate 0 is c3, candidates 1 and 2 are
+// the two midpoints the NEXT step asks for if it bisects, candidates 3..6 the four midpoints the step after that
+// can ask for if both bisect (refine_guess; search_consume uses a value only if the step asks for exactly that velocity).
+BH_HD double refine_guess(double c1, double c2, double c3, int i) {
+  const double g1 = 0.5 * (c1 + c3), g2 = 0.5 * (c3 + c2);
+  switch (i) {
+    case 1: return g1;
+    case 2: return g2;
+    case 3: return 0.5 * (c1 + g1);
+    case 4: return 0.5 * (g1 + c3);
+    case 5: return 0.5 * (c3 + g2);
+    default: return 0.5 * (g2 + c2);
+  }
+}
+BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i, double c2r = 0.0) {
+  if (stage > ST_BR_STEP) return i == 0 ? c : refine_guess(clow, c2r, c, i);
   if (stage == ST_BR_FIRST) {            // c1 itself, then the upward walk from it
     if (i == 0) return c;
     idir = +1;
@@ -980,6 +994,13 @@ BH_HD double search_pending_c(const Search& s) {
 // order), total = lanes in use.  Closed form from the two masks -- no scan, no integer division:
 // (extra + 0.5) / nbr stays >= 1/64 away from every integer for 0 <= extra <= 32, 1 <= nbr <= 32, far beyond
 // the error of the approximate fp32 quotient.
+// When lanes are left over even after every walking chain has four (small batches, deep models), each refining chain gets
+// kRefineGuesses more for the two midpoints its next step may ask for, or kRefineGuesses2 for those of its next two
+// steps (search_consume).
+constexpr int kRefineGuesses = 2, kRefineGuesses2 = 6;
+#ifndef BH_GUESS_WALK_EXTRA
+#define BH_GUESS_WALK_EXTRA 3
+#endif
 struct LaneDeal { int cnt, excl, total; };
 BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_spec) {
 #if defined(__CUDA_ARCH__)
@@ -988,7 +1009,10 @@ BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_s
 #define BH_POPC(x) __builtin_popcount(x)
 #endif
   const int nact = BH_POPC(active), nbr = BH_POPC(bracket);
-  const int extra = 32 - nact;
+  const int nrf = nact - nbr;
+  const int room = 32 - nact - BH_GUESS_WALK_EXTRA * nbr;
+  const int g = nrf == 0 ? 0 : (kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0));
+  const int extra = 32 - nact - g * nrf;
 #if defined(__CUDA_ARCH__)
   const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
 #else
@@ -999,16 +1023,18 @@ BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_s
   const bool capped = per >= max_spec;
   const unsigned below = (1u << lane) - 1u;
   const int rank = BH_POPC(bracket & below);
+  const int act_below = BH_POPC(active & below);
   const unsigned me = 1u << lane;
   LaneDeal d;
   d.cnt = 0;
   if (active & me) {
-    d.cnt = 1;
+    d.cnt = 1 + g;
     if (bracket & me) { d.cnt = per + (rank < rem ? 1 : 0); if (d.cnt > max_spec) d.cnt = max_spec; }
   }
-  // walking chains below this lane hold rank * per + min(rank, rem) lanes (or rank * max_spec when capped)
-  d.excl = BH_POPC(active & below) - rank + (capped ? rank * max_spec : rank * per + (rank < rem ? rank : rem));
-  d.total = nact - nbr + (capped ? nbr * max_spec : nbr * per + (nbr < rem ? nbr : rem));
+  // walking chains below this lane hold rank * per + min(rank, rem) lanes (or rank * max_spec when capped),
+  // refining chains below it 1 + g each
+  d.excl = (act_below - rank) * (1 + g) + (capped ? rank * max_spec : rank * per + (rank < rem ? rank : rem));
+  d.total = nrf * (1 + g) + (capped ? nbr * max_spec : nbr * per + (nbr < rem ? nbr : rem));
 #undef BH_POPC
   return d;
 }
@@ -1124,7 +1150,7 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
 // this round (n = 1 unless stage == ST_BR_STEP).  Returns how many of the n
 // values were consumed (the rest was speculation past a sign change or past
 // the search window).
-BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& ctx) {
+BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& ctx, const bool guesses = true) {
   int first = 0;
   switch (s.stage) {
     case ST_BR_FIRST: {
@@ -1160,10 +1186,31 @@ BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& c
     }
     case ST_RF_TOP:
     case ST_RF_POST: {
+      // values 1 and 2 (if dealt) belong to the midpoints of the two half brackets this step can leave behind
+      const double o1 = s.c1, o2 = s.c2, o3 = s.c3;
       s.del3 = del[0];
-      if (nevill_resume(s, s.stage == ST_RF_TOP))
-        search_root_end(s, ctx, s.c3, !(s.c3 > s.betmx));                // :475-476
-      return 1;
+      int used = 1;
+      bool done = nevill_resume(s, s.stage == ST_RF_TOP);
+      if (guesses && !done && n > kRefineGuesses) {
+        // the step bisected into one of the two half brackets: its value is here already
+        const int i1 = s.c3 == refine_guess(o1, o2, o3, 1) ? 1 : (s.c3 == refine_guess(o1, o2, o3, 2) ? 2 : 0);
+        if (i1) {
+          s.del3 = del[i1];
+          used = 2;
+          done = nevill_resume(s, s.stage == ST_RF_TOP);
+          if (!done && n > kRefineGuesses2) {
+            const int ia = 2 * i1 + 1, ib = ia + 1;              // the two halves of that half
+            const int i2 = s.c3 == refine_guess(o1, o2, o3, ia) ? ia : (s.c3 == refine_guess(o1, o2, o3, ib) ? ib : 0);
+            if (i2) {
+              s.del3 = del[i2];
+              used = 3;
+              done = nevill_resume(s, s.stage == ST_RF_TOP);
+            }
+          }
+        }
+      }
+      if (done) search_root_end(s, ctx, s.c3, !(s.c3 > s.betmx));        // :475-476
+      return used;
     }
     default:
       return 0;

@@ -45,7 +45,8 @@ namespace {
 
 struct WarpShared {
   double c[32];       // pending candidate base (c1 or c3) per owner
-  double clow[32];
+  double clow[32];    // walking chain: lower end of the window; refining chain: c1
+  double c2[32];      // refining chain: c2
   double omega[32];
   double del[32];     // secular values per lane
   double omA[SWD_MAX_PERIODS], omB[SWD_MAX_PERIODS];   // per-period angular frequencies of this curve
@@ -222,7 +223,8 @@ swd_kernel(SwdLaunch p) {
     const unsigned excl = (unsigned)deal.excl, total = (unsigned)deal.total;
     if (cnt > 0) {
       ws->c[lane] = search_pending_c(s);
-      ws->clow[lane] = s.clow;
+      ws->clow[lane] = s.stage > ST_BR_STEP ? s.c1 : s.clow;
+      ws->c2[lane] = s.c2;
       ws->omega[lane] = s.omega;
       ws->stage[lane] = s.stage;
       ws->idir[lane] = s.idir;
@@ -241,7 +243,7 @@ swd_kernel(SwdLaunch p) {
       int i = lane - start;
       int own = ws->owner_at[start];
       double omega = ws->omega[own];
-      double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i);
+      double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i, ws->c2[own]);
       int L = ws->nlay[own];
       double wvno = fm::div(omega, c);
       ws->del[lane] = secular_rec(wave, rec + ws->col[own], fs, S, L, wvno, omega);

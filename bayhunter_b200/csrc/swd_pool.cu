@@ -210,7 +210,7 @@ swd_pool_kernel(SwdLaunch p, int M) {
     // ---- phase C: owners consume their values in reference order ----
     if (t < kPoolWarps) ws->startbits[t] = 0u;
     if (t == 0) ws->any_wait = 0;
-    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx);
+    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx, false);   // a full batch has no lanes for refinement guesses
     BH_TICK(6)
     __syncthreads();
     BH_TICK(7)

@@ -77,10 +77,14 @@ int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, c
       Search& s = m[r];
       int nmax = spec_mode == 0 ? 1 : (spec_mode > 0 ? spec_mode : 1 + (int)(lcg(rng) % 32));
       n[r] = search_nwant(s, nmax);
+      // a refining chain with lanes to spare also gets the two midpoints its next step may ask for (deal_lanes)
+      const bool refining = s.stage == ST_RF_TOP || s.stage == ST_RF_POST;
+      if (refining && spec_mode != 0 && (spec_mode > 0 ? spec_mode >= 3 : (lcg(rng) & 1)))
+        n[r] = 1 + ((spec_mode > 0 ? spec_mode >= 7 : (lcg(rng) & 1)) ? kRefineGuesses2 : kRefineGuesses);
       any += n[r];
       double cpub = search_pending_c(s);
       for (int i = 0; i < n[r]; ++i) {
-        double c = candidate_from(s.stage, cpub, s.idir, s.clow, s.dc, i);
+        double c = candidate_from(s.stage, cpub, s.idir, refining ? s.c1 : s.clow, s.dc, i, s.c2);
         del[r][i] = secular(wave, rows.data(), 1, nlayer, s.omega / c, s.omega);
         ++evaluated;
       }
