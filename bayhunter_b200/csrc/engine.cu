@@ -603,6 +603,15 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       const long long chains = (long long)B * (nph + 2 * ngr);
       long long target = chains / 14;
       if (target > 2400) target = 2400;
+      // below a full machine, lanes beyond the chains' own pay twice -- bracket steps and refinement guesses
+      // (swd_core.cuh: deal_lanes): about 4 chains per warp up to ~11 warps per SM (profiles/r02_swd_restructure.txt
+      // section 14: joint5 B = 1024 1.75 -> 1.38 ms, B = 2048 2.03 -> 1.76, swd2 B = 4096 1.68 -> 1.48)
+      {
+        long long t2 = chains / 4;
+        const long long cap2 = e->nsm > 0 ? 11LL * e->nsm + e->nsm / 8 : 1650;
+        if (t2 > cap2) t2 = cap2;
+        if (target < t2) target = t2;
+      }
       // small batches: the chains are the critical path and the machine is far from full -- one warp per SM
       // sub-partition (as long as a warp keeps two chains) before chains are packed 14 to a warp
       // (profiles/r01_variants.txt: joint5 B = 256 / 512 / 1024: 1.81 -> 1.49 / 1.58 / 1.72 ms)
