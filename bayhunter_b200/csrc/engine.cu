@@ -500,22 +500,21 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     gen.mode[c] = d.mode; gen.flsph[c] = d.flsph;
     gen.periods[c] = d.periods; gen.curve_off[c] = e->curve_off[t];
   }
-  // The pool kernel (swd_pool.cu) pays when its CTAs fill the device four to an SM: -4.5 % at 16 k (model, wave type)
-  // pairs, -9 % at 32 k, slower below ~8 k (profiles/r02_swd_restructure.txt section 12).
+  // The pool kernel (swd_pool.cu) pays when its CTAs fill the device four to an SM: -5 % at 8 k (model, wave type) pairs
+  // (14 models per CTA, lanes to spare for refinement guesses), -5 % at 16 k (28 models per CTA), -9 % at 32 k; slower
+  // below ~6 k pairs and with one wave type only (profiles/r02_swd_restructure.txt sections 12, 15).
   int pool_m = 0;
   if (e->pool != 0 && nswd > 0) {
     const int nl = (swl[0].ncurves > 0) + (swl[1].ncurves > 0);
-    bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : (nl == 2 && e->concurrent)) && !e->lockstep;   // rule: Rayleigh and Love CTAs side by side (one wave type alone: 3.09 vs 3.02 ms, swd2 at B = 16384)
+    // rule: Rayleigh and Love CTAs side by side (one wave type alone: 3.09 vs 3.02 ms, swd2 at B = 16384)
+    bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : (nl == 2 && e->concurrent)) && !e->lockstep;
     for (int w = 0; w < 2; ++w) fits = fits && (swl[w].ncurves == 0 || swd_pool_fits(swl[w]));
     const long long slots = 4LL * e->nsm, pairs = (long long)B * nl;
-    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && pairs * 10 >= slots * 28 * 9 &&
-                                  swd_pool_smem_bytes(lmax, 28) * 4 <= (size_t)220 * 1024))) {
-      pool_m = e->pool_models;
-      if (pool_m <= 0) {
-        pool_m = slots > 0 ? (int)((pairs + slots - 1) / slots) : 28;
-        pool_m = pool_m < 28 ? 28 : (pool_m > 32 ? 32 : pool_m);
-      }
-    }
+    int m = slots > 0 ? (int)((pairs + slots - 1) / slots) : 28;
+    m = m < 14 ? 14 : (m > 32 ? 32 : m);
+    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && pairs * 10 >= slots * 14 * 9 &&
+                                  swd_pool_smem_bytes(lmax, m) * 4 <= (size_t)220 * 1024)))
+      pool_m = e->pool_models > 0 ? e->pool_models : m;
   }
   if (!e->split_waves && pool_m == 0 && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
     // one mixed launch: append the Love curves to the Rayleigh launch

@@ -29,12 +29,15 @@ namespace {
 #ifndef BH_POOL_MIN_BLOCKS
 #define BH_POOL_MIN_BLOCKS 4
 #endif
+#ifndef BH_POOL_GUESS_MAX_CHAINS
+#define BH_POOL_GUESS_MAX_CHAINS 72
+#endif
 constexpr int kPoolWarps = BH_POOL_WARPS;
 constexpr int kPoolLanes = kPoolWarps * 32;
 constexpr int kPoolMaxModels = kPoolLanes;      // links / first-root mailboxes per CTA
 
 struct PoolShared {
-  double c[kPoolLanes], clow[kPoolLanes], omega[kPoolLanes], del[kPoolLanes];
+  double c[kPoolLanes], clow[kPoolLanes], c2[kPoolLanes], omega[kPoolLanes], del[kPoolLanes];
   double omA[SWD_MAX_PERIODS], omB[SWD_MAX_PERIODS], omP[SWD_MAX_PERIODS];
   SearchLink link[kPoolMaxModels];
   int stage[kPoolLanes], idir[kPoolLanes], nlay[kPoolLanes], col[kPoolLanes], owner_at[kPoolLanes];
@@ -45,7 +48,8 @@ struct PoolShared {
 };
 
 // kWave: 1 Love, 2 Rayleigh (all curves of a launch are of one wave type)
-template <int kWave>
+// kGuess: refining chains take lanes for refinement guesses when the CTA has lanes to spare (M well below 28)
+template <int kWave, bool kGuess>
 __global__ void __launch_bounds__(kPoolLanes, BH_POOL_MIN_BLOCKS)
 swd_pool_kernel(SwdLaunch p, int M) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -165,21 +169,28 @@ swd_pool_kernel(SwdLaunch p, int M) {
     act_below += __popc(a_w & below);
     rank += __popc(b_w & below);
     // dealing rule of swd_core.cuh (deal_lanes), over the CTA's lanes
-    const int extra = kPoolLanes - nact;
+    const int nrf = nact - nbr;
+    int g = 0;
+    if (kGuess && nrf > 0) {
+      const int room = kPoolLanes - nact - BH_GUESS_WALK_EXTRA * nbr;
+      g = kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0);
+    }
+    const int extra = kPoolLanes - nact - g * nrf;
     const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
     const int rem = extra - quo * nbr;
     const int per = quo + 1;
     const bool capped = per >= max_spec;
     int cnt = 0;
     if (want > 0) {
-      cnt = 1;
+      cnt = 1 + g;
       if (want > 1) { cnt = per + (rank < rem ? 1 : 0); if (cnt > max_spec) cnt = max_spec; }
     }
-    const int excl = act_below - rank + (capped ? rank * max_spec : rank * per + (rank < rem ? rank : rem));
-    const int total = nact - nbr + (capped ? nbr * max_spec : nbr * per + (nbr < rem ? nbr : rem));
+    const int excl = (act_below - rank) * (1 + g) + (capped ? rank * max_spec : rank * per + (rank < rem ? rank : rem));
+    const int total = nrf * (1 + g) + (capped ? nbr * max_spec : nbr * per + (nbr < rem ? nbr : rem));
     if (cnt > 0) {
       ws->c[t] = search_pending_c(s);
-      ws->clow[t] = s.clow;
+      ws->clow[t] = (kGuess && s.stage > ST_BR_STEP) ? s.c1 : s.clow;
+      if (kGuess) ws->c2[t] = s.c2;
       ws->omega[t] = s.omega;
       ws->stage[t] = s.stage;
       ws->idir[t] = s.idir;
@@ -199,7 +210,7 @@ swd_pool_kernel(SwdLaunch p, int M) {
       const int i = t - start;
       const int own = ws->owner_at[start];
       const double omega = ws->omega[own];
-      const double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i);
+      const double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i, kGuess ? ws->c2[own] : 0.0);
       ws->del[t] = secular_rec(wave, rec + ws->col[own], fs, M, ws->nlay[own], fm::div(omega, c), omega);
       evaluated += 1;
     }
@@ -210,7 +221,7 @@ swd_pool_kernel(SwdLaunch p, int M) {
     // ---- phase C: owners consume their values in reference order ----
     if (t < kPoolWarps) ws->startbits[t] = 0u;
     if (t == 0) ws->any_wait = 0;
-    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx, false);   // a full batch has no lanes for refinement guesses
+    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx, kGuess);
     BH_TICK(6)
     __syncthreads();
     BH_TICK(7)
@@ -256,23 +267,23 @@ size_t pool_smem_bytes(int lcap, int M) {
   return (size_t)SWD_REC_FIELDS * lcap * M * sizeof(double) + sizeof(PoolShared);
 }
 
-template <int kWave>
+template <int kWave, bool kGuess>
 void launch_pool(const SwdLaunch& p, int M, cudaStream_t st) {
   const int nb = (p.B + M - 1) / M;
   const size_t smem = pool_smem_bytes(p.lcap, M);
   static KernelAttrs attrs;
-  bh_configure_kernel(swd_pool_kernel<kWave>, smem, attrs);
+  bh_configure_kernel(swd_pool_kernel<kWave, kGuess>, smem, attrs);
   static bool reported = false;
   if (!reported && getenv("BH_DEBUG")) {
     reported = true;
     int res = -1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, swd_pool_kernel<kWave>, kPoolLanes, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, swd_pool_kernel<kWave, kGuess>, kPoolLanes, smem);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, swd_pool_kernel<kWave>);
-    fprintf(stderr, "[bh] swd_pool_kernel<%d>: %d CTAs of %d lanes, %d models each, smem %zu B, regs %d, local %zu B, max resident CTAs/SM %d\n",
-            kWave, nb, kPoolLanes, M, smem, fa.numRegs, fa.localSizeBytes, res);
+    cudaFuncGetAttributes(&fa, swd_pool_kernel<kWave, kGuess>);
+    fprintf(stderr, "[bh] swd_pool_kernel<%d,%d>: %d CTAs of %d lanes, %d models each, smem %zu B, regs %d, local %zu B, max resident CTAs/SM %d\n",
+            kWave, (int)kGuess, nb, kPoolLanes, M, smem, fa.numRegs, fa.localSizeBytes, res);
   }
-  swd_pool_kernel<kWave><<<nb, kPoolLanes, smem, st>>>(p, M);
+  swd_pool_kernel<kWave, kGuess><<<nb, kPoolLanes, smem, st>>>(p, M);
 }
 
 }  // namespace
@@ -305,7 +316,12 @@ int swd_pool_warp_count(const SwdLaunch& p, int M) { return kPoolWarps * ((p.B +
 
 void launch_swd_pool(const SwdLaunch& p, int M, cudaStream_t st) {
   if (p.ncurves <= 0 || p.B <= 0) return;
-  if (p.wave[0] == 2) launch_pool<2>(p, M, st); else launch_pool<1>(p, M, st);
+  // refinement guesses need 3 lanes per refining + 4 per walking chain: no room from ~24 models (72 chains) up
+  int cpm = 0;
+  for (int c = 0; c < p.ncurves; ++c) cpm += p.igr[c] ? 2 : 1;
+  const bool guess = M * cpm <= BH_POOL_GUESS_MAX_CHAINS;
+  if (p.wave[0] == 2) { if (guess) launch_pool<2, true>(p, M, st); else launch_pool<2, false>(p, M, st); }
+  else { if (guess) launch_pool<1, true>(p, M, st); else launch_pool<1, false>(p, M, st); }
 }
 
 }  // namespace bh

@@ -35,7 +35,7 @@ def test_lockstep_kernel_is_bit_identical(cfg, B):
             assert np.array_equal(a, b, equal_nan=True), (cfg, grp, ph)
 
 
-@pytest.mark.parametrize("cfg,B", [("joint5", 700), ("transd3", 300), ("swd2", 257), ("joint5", 5), ("joint5", 8192)])
+@pytest.mark.parametrize("cfg,B", [("joint5", 700), ("transd3", 300), ("swd2", 257), ("joint5", 5), ("joint5", 4200), ("joint5", 8192)])
 def test_pool_kernel_is_bit_identical(cfg, B):
     """swd_pool_kernel (a CTA's 128 lanes dealt over the chains of M models) consumes swd_kernel's candidate sequence;
     at BASELINE's full batch (joint5, 8192 chains) the engine's rule picks it."""
