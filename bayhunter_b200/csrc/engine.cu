@@ -607,7 +607,9 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       // section 14: joint5 B = 1024 1.75 -> 1.38 ms, B = 2048 2.03 -> 1.76, swd2 B = 4096 1.68 -> 1.48)
       {
         long long t2 = chains / 4;
-        const long long cap2 = e->nsm > 0 ? 11LL * e->nsm + e->nsm / 8 : 1650;
+        // (deep models -- long evaluations, relatively cheap bookkeeping -- take lanes up to 14 warps per SM: transd3
+        //  B = 4096 6.79 -> 6.46 ms)
+        const long long cap2 = e->nsm > 0 ? (lmax > 12 ? 14LL : 11LL) * e->nsm + e->nsm / 8 : 1650;
         if (t2 > cap2) t2 = cap2;
         if (target < t2) target = t2;
       }
