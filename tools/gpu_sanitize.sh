@@ -41,7 +41,7 @@ rows, nlay = synthetic.draw_batch(70, (3, 7), seed=5)
 noise = synthetic.draw_noise(70, ("rdispgr", "rdispph", "ldispgr", "ldispph"), seed=6)
 eng2.set(swd_pool=0)
 a = eng2.eval_host(rows, nlay, noise)
-for m in (0, 9):
+for m in (0, 9, 28):
     eng2.set(swd_pool=1, swd_pool_models=m)
     b = eng2.eval_host(rows, nlay, noise)
     assert np.array_equal(a[0], b[0])
