@@ -136,6 +136,13 @@ int bh_engine_is_tuning(const bh_engine* e);
  *                                        items (the rest take Love; 0 = no partition, the default)
  *   key "swd_split_waves"        0/1     Rayleigh and Love curves in one launch (default) or two
  *   key "swd_max_spec"           1..32   speculative bracket candidates per search
+ *   key "swd_pool"               -1/0/1  dispersion by swd_pool_kernel (a CTA's 128 lanes dealt over all chains of M
+ *                                        models of one wave type, Rayleigh and Love launches side by side): by rule
+ *                                        (default: both wave types present, >= ~3.7 k models per GPU), never, always
+ *                                        (results do not depend on it)
+ *   key "swd_pool_models"        0..128  M of the above (0 = rule: models x wave types / (4 x SMs), 14..32)
+ *   key "swd_lockstep"           0/1     dispersion by swd_lockstep_kernel (every lane owns a chain; a measured
+ *                                        negative result at these batch sizes, default 0)
  *   key "rf_prune_exp10"         0..300  receiver function: spectral bins whose Gauss-filter weight
  *                                        exp(-(w/2a)^2) is below 10^-value are not computed (they enter the
  *                                        inverse transform as 0); default 30, i.e. 1e-30 of the passband --
