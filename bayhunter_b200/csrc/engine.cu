@@ -112,7 +112,7 @@ struct bh_engine {
   int* swd_done = nullptr;    // retired dispersion warps of the current evaluation
   // Spectral bins whose Gauss-filter weight exp(-(w/2a)^2) is below this are not computed: next to a
   // trace peak of order 0.1-1 they are below the resolution of fp64 (1e-30 vs 2e-16).  0 = all bins.
-  double rf_floor = 1e-30;
+  double rf_floor = 1e-20;    // Gauss-filter weight below which a spectral bin is not computed (4 orders below fp64 resolution of the trace)
   int nsm = 0;
   int max_nfreq = 0;
   // Host-pointer entry points: two slots of pinned staging + device mirrors, so that the copies of call

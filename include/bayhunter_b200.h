@@ -145,8 +145,9 @@ int bh_engine_is_tuning(const bh_engine* e);
  *                                        negative result at these batch sizes, default 0)
  *   key "rf_prune_exp10"         0..300  receiver function: spectral bins whose Gauss-filter weight
  *                                        exp(-(w/2a)^2) is below 10^-value are not computed (they enter the
- *                                        inverse transform as 0); default 30, i.e. 1e-30 of the passband --
- *                                        far below fp64 resolution of the trace; 0 computes every bin
+ *                                        inverse transform as 0); default 20, i.e. 1e-20 of the passband --
+ *                                        four orders of magnitude below fp64 resolution of the trace; 0 computes
+ *                                        every bin
  *   key "rf_gate_pct"            0..100  the forked RF stream starts once this share of the dispersion
  *                                        warps has retired (default 25; 0: no gate, the streams race)
  *   key "concurrent"             0/1     run SWD and RF kernels on forked streams

@@ -476,9 +476,9 @@ def test_adaptive_record_capacity_never_changes_results():
 
 
 def test_rf_spectral_pruning_is_below_fp64_resolution(oracle):
-    """The spectrum kernel skips frequency bins whose Gauss-filter weight is < 1e-30 (default).  The
-    traces must equal the all-bins computation to ~1e-25 of the peak (they differ by terms that are
-    < 1e-30 of the passband), and both must match the oracle within the RF tolerance."""
+    """The spectrum kernel skips frequency bins whose Gauss-filter weight is < 1e-20 (default).  The
+    traces must equal the all-bins computation to ~1e-17 of the peak (they differ by terms that are
+    < 1e-20 of the passband; < 1e-24 with the floor at 1e-30), and match the oracle within the RF tolerance."""
     from bayhunter_b200 import Engine, TargetSpec, synthetic
     x = synthetic.rf_time_axis(dict(n=512, dt=0.1, t0=-5.0))
     B = 64
@@ -487,15 +487,17 @@ def test_rf_spectral_pruning_is_below_fp64_resolution(oracle):
         spec = [TargetSpec("prf", x, np.zeros(x.size), cov="exp", gauss=gauss)]
         noise = synthetic.draw_noise(B, ["prf"], seed=6)
         eng = Engine(spec, B, rows.shape[1])
+        default = eng.eval_host(rows, nlay, noise, want_synth=True)[3]
         eng.set(rf_prune_exp10=0)
         full = eng.eval_host(rows, nlay, noise, want_synth=True)[3]
         eng.set(rf_prune_exp10=30)
         pruned = eng.eval_host(rows, nlay, noise, want_synth=True)[3]
         peak = np.abs(full).max(axis=1, keepdims=True)
         assert (np.abs(pruned - full) / peak).max() <= 1e-24, gauss
+        assert (np.abs(default - full) / peak).max() <= 2e-17, gauss
         h, vp, vs, rho = synthetic.unpack(rows[3], int(nlay[3]))
         _, yo = oracle.recfunc(h, vp, vs, rho, x, gauss=gauss)
-        assert np.abs(pruned[3] - yo).max() / np.abs(yo).max() <= 1e-9
+        assert np.abs(default[3] - yo).max() / np.abs(yo).max() <= 1e-9
 
 
 def test_rf_plugin_per_layer_q(oracle):
