@@ -11,9 +11,11 @@
 //   * group chains (32 chains on 32 lanes in swd_kernel: no lane to spare) borrow the lanes phase chains leave;
 //   * a model's layer records are built once for its three chains;
 //   * 125 registers (Rayleigh), M = 28: 4 CTAs = 16 warps per SM, 586 CTAs on 592 slots at B = 8192.
-// Measured (joint5, B = 8192): 3.64 -> 3.45 ms per evaluation; B = 16384: 7.14 -> 6.47 ms; below ~8 k (model,
-// wave type) pairs the CTAs no longer fill the device and swd_kernel with its autotuned layout is faster, so
-// the engine picks this kernel by rule (engine.cu) -- profiles/r02_swd_restructure.txt section 12.
+// Measured (joint5): B = 8192 3.64 -> 3.45 ms per evaluation (M = 28), B = 16384 7.14 -> 6.47 (M = 32), B = 4096
+// 2.55 -> 2.42 (M = 14: the kGuess instantiation, whose spare lanes go to the refining chains' next midpoints,
+// swd_core.cuh: refine_guess); below ~7 k (model, wave type) pairs the CTAs no longer fill the device and
+// swd_kernel with its fitted layout is faster, so the engine picks this kernel by rule (engine.cu) --
+// profiles/r02_swd_restructure.txt sections 12 and 15.
 #include <stdio.h>
 #include <stdlib.h>
 
