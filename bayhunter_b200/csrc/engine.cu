@@ -506,13 +506,17 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   int pool_m = 0;
   if (e->pool != 0 && nswd > 0) {
     const int nl = (swl[0].ncurves > 0) + (swl[1].ncurves > 0);
-    // rule: Rayleigh and Love CTAs side by side (one wave type alone: 3.09 vs 3.02 ms, swd2 at B = 16384)
-    bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : (nl == 2 && e->concurrent)) && !e->lockstep;
+    // rule: Rayleigh and Love CTAs side by side (one wave type alone: equal at best for shallow models -- swd2 B = 4096
+    // 1.48 / 1.48 ms, B = 16384 3.02 / 3.09), or deep models, whose long evaluations make the shared lanes pay with one
+    // wave type too (transd3 B = 4096 6.34 -> 5.80 ms at 8 models per CTA, B = 8192 9.49 -> 7.70 at 14)
+    const bool deep = lmax > 12;
+    bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : ((nl == 2 && e->concurrent) || (nl == 1 && deep))) && !e->lockstep;
     for (int w = 0; w < 2; ++w) fits = fits && (swl[w].ncurves == 0 || swd_pool_fits(swl[w]));
     const long long slots = 4LL * e->nsm, pairs = (long long)B * nl;
+    const int mlo = (nl == 1 && deep) ? 8 : 14;
     int m = slots > 0 ? (int)((pairs + slots - 1) / slots) : 28;
-    m = m < 14 ? 14 : (m > 32 ? 32 : m);
-    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && pairs * 10 >= slots * 14 * 9 &&
+    m = m < mlo ? mlo : (m > 32 ? 32 : m);
+    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && pairs * 100 >= slots * mlo * (deep ? 85 : 90) &&
                                   swd_pool_smem_bytes(lmax, m) * 4 <= (size_t)220 * 1024)))
       pool_m = e->pool_models > 0 ? e->pool_models : m;
   }
