@@ -503,7 +503,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
   // The pool kernel (swd_pool.cu) pays when its CTAs fill the device four to an SM: -5 % at 8 k (model, wave type) pairs
   // (14 models per CTA, lanes to spare for refinement guesses), -5 % at 16 k (28 models per CTA), -9 % at 32 k; slower
   // below ~6 k pairs and with one wave type only (profiles/r02_swd_restructure.txt sections 12, 15).
-  int pool_m = 0;
+  int pool_cpc = 0;      // chains per CTA of the pool kernel; 0: swd_kernel
   if (e->pool != 0 && nswd > 0) {
     const int nl = (swl[0].ncurves > 0) + (swl[1].ncurves > 0);
     // rule: Rayleigh and Love CTAs side by side (one wave type alone: equal at best for shallow models -- swd2 B = 4096
@@ -512,15 +512,25 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     const bool deep = lmax > 12;
     bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : ((nl == 2 && e->concurrent) || (nl == 1 && deep))) && !e->lockstep;
     for (int w = 0; w < 2; ++w) fits = fits && (swl[w].ncurves == 0 || swd_pool_fits(swl[w]));
-    const long long slots = 4LL * e->nsm, pairs = (long long)B * nl;
-    const int mlo = (nl == 1 && deep) ? 8 : 14;
-    int m = slots > 0 ? (int)((pairs + slots - 1) / slots) : 28;
-    m = m < mlo ? mlo : (m > 32 ? 32 : m);
-    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && pairs * 100 >= slots * mlo * (deep ? 85 : 90) &&
-                                  swd_pool_smem_bytes(lmax, m) * 4 <= (size_t)220 * 1024)))
-      pool_m = e->pool_models > 0 ? e->pool_models : m;
+    // counted in chains (3 per model with a group and a phase curve): 42..96 chains per CTA (14..32 such models), from 24
+    // for deep models with one wave type; as many chains per CTA as fill four CTAs per SM
+    long long chains = 0;
+    int cpm_max = 1;
+    for (int w = 0; w < 2; ++w) {
+      int cpm = 0;
+      for (int c = 0; c < swl[w].ncurves; ++c) cpm += swl[w].igr[c] ? 2 : 1;
+      chains += (long long)B * cpm;
+      if (cpm > cpm_max) cpm_max = cpm;
+    }
+    const long long slots = 4LL * e->nsm;
+    const int clo = (nl == 1 && deep) ? 24 : 42;
+    int cpc = slots > 0 ? (int)((chains + slots - 1) / slots) : 84;
+    cpc = cpc < clo ? clo : (cpc > 96 ? 96 : cpc);
+    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && chains * 100 >= slots * clo * (deep ? 85 : 90) &&
+                                  swd_pool_smem_bytes(lmax, (cpc + cpm_max - 1) / cpm_max) * 4 <= (size_t)220 * 1024)))
+      pool_cpc = cpc;
   }
-  if (!e->split_waves && pool_m == 0 && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
+  if (!e->split_waves && pool_cpc == 0 && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
     // one mixed launch: append the Love curves to the Rayleigh launch
     SwdLaunch& a = swl[0];
     const SwdLaunch& b = swl[1];
@@ -770,8 +780,14 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
           sw.type_quota[1] = (int)((wl + (e->nsm - split) - 1) / (e->nsm - split));
           BH_CUDA(cudaMemsetAsync(e->swd_queue, 0, (2 + e->nsm) * sizeof(int), sst));
         }
-        const bool pool = pool_m > 0;
-        const int pm = pool ? swd_pool_models(sw, lc, pool_m) : 0;
+        const bool pool = pool_cpc > 0;
+        int pm = 0;
+        if (pool) {
+          int cpm = 0;
+          for (int c = 0; c < sw.ncurves; ++c) cpm += sw.igr[c] ? 2 : 1;
+          const int want = e->pool_models > 0 ? e->pool_models : (pool_cpc + cpm - 1) / cpm;
+          pm = swd_pool_models(sw, lc, want);
+        }
         if (pool) sw.queue = nullptr;
         gate_warps += pool ? swd_pool_warp_count(sw, pm) : swd_warp_count(sw);
         auto go = [&]() {

@@ -54,6 +54,35 @@ def test_pool_kernel_is_bit_identical(cfg, B):
             assert np.array_equal(a, b, equal_nan=True), (cfg, m)
 
 
+@pytest.mark.parametrize("refs,nrows,B", [(("ldispph", "ldispgr"), (3, 31), 4300),          # Love only, deep: pool by rule
+                                          (("rdispph", "rdispgr", "ldispph", "ldispgr"), (3, 31), 4000),   # both waves, deep
+                                          (("rdispgr", "ldispgr"), 6, 4100),                 # group curves only
+                                          (("rdispph", "ldispph"), 6, 4100),                 # phase curves only
+                                          (("rdispph", "rdispph", "ldispgr"), 6, 4100)])     # two phase curves of a wave: no pool
+def test_pool_rule_on_other_curve_sets(refs, nrows, B):
+    """The engine's kernel rule on curve sets outside the BASELINE configurations: whatever it picks equals swd_kernel."""
+    from bayhunter_b200 import Engine, synthetic
+    rng = np.random.default_rng(43)
+    specs, _ = _make_targets(refs, np.linspace(1, 40, 18), None, rng)
+    rows, nlay = synthetic.draw_batch(B, nrows, seed=44)
+    noise = synthetic.draw_noise(B, refs, seed=45)
+    eng = Engine(specs, B, rows.shape[1])
+    eng.set(swd_pool=0, profile=1)
+    base = eng.eval_host(rows, nlay, noise, want_synth=True)
+    cons0, _ = eng.last_counts()
+    eng.set(swd_pool=-1)
+    out = eng.eval_host(rows, nlay, noise, want_synth=True)
+    cons, ev = eng.last_counts()
+    picked_pool = "swd_pool" in eng.last_kernel_ms() or "swd_pool_love" in eng.last_kernel_ms()
+    if nrows != 6:
+        assert picked_pool, "deep models: the rule takes the pool kernel"
+    if len(set(refs)) != len(refs):
+        assert not picked_pool, "two curves of one kind in a wave type: swd_kernel"
+    assert cons == cons0 and ev >= cons
+    for a, b in zip(out, base):
+        assert np.array_equal(a, b, equal_nan=True), refs
+
+
 def test_async_host_entry_overlaps_and_matches():
     """bh_engine_eval_host_async / bh_engine_wait with pageable numpy buffers, two calls in flight."""
     eng, specs, _, rows, nlay, noise = _engine("joint5", 512, 50)
