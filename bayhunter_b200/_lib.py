@@ -73,6 +73,8 @@ SIGNATURES = {
     "bh_engine_destroy": (None, [ctypes.c_void_p]),
     "bh_engine_synth_stride": (ctypes.c_int, [ctypes.c_void_p]),
     "bh_engine_is_tuning": (ctypes.c_int, [ctypes.c_void_p]),
+    "bh_engine_capture_begin": (ctypes.c_int, [ctypes.c_void_p]),
+    "bh_engine_capture_end": (ctypes.c_int, [ctypes.c_void_p]),
     "bh_engine_set": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "bh_engine_eval": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 4 +
                        [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5),

@@ -136,8 +136,8 @@ struct bh_engine {
   bool slots_ready = false;
   long long next_ticket = 1;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  cudaStream_t s_own = nullptr, s_aux = nullptr, s_aux2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_fork2 = nullptr;
+  cudaStream_t s_own = nullptr, s_aux = nullptr, s_aux2 = nullptr, s_aux3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_fork2 = nullptr, ev_join3 = nullptr, ev_fork3 = nullptr;
   // tunables
   int searches_per_warp = 0;  // phase-velocity curves; 0 = auto
   int group_spw = 0;          // group-velocity curves; 0 = half of the above
@@ -148,6 +148,7 @@ struct bh_engine {
   int direct = 0;             // 0 never, 1 when warps are full of chains, 2 always
   int lockstep = 0;           // swd_lockstep_kernel (every lane owns a chain, pairwise guesses): 0 off, 1 on.  Measured
                               // equal or slower than swd_kernel on every BASELINE configuration (profiles/r02_swd_restructure.txt)
+  int graph_safe = 0;         // between bh_engine_capture_begin / _end: evaluations enqueue stream-ordered work only
   int pool = -1;              // swd_pool_kernel (a CTA's 128 lanes dealt over the chains of ~28 models): 0 off, 1 on, -1 rule (full batches)
   int pool_models = 0;        // models per CTA of the pool kernel (0 = rule)
   int ls_spw[2] = {0, 0};     // lockstep kernel: models per warp of group / phase curves (0 = rule)
@@ -217,6 +218,8 @@ void bh_engine_destroy(bh_engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
+  if (e->ev_join3) cudaEventDestroy(e->ev_join3);
+  if (e->ev_fork3) cudaEventDestroy(e->ev_fork3);
   if (e->ev_maxn) cudaEventDestroy(e->ev_maxn);
   for (cudaEvent_t ev : e->ev_tune) if (ev) cudaEventDestroy(ev);
   if (e->h_maxn) cudaFreeHost(e->h_maxn);
@@ -234,6 +237,7 @@ void bh_engine_destroy(bh_engine* e) {
   if (e->s_own) cudaStreamDestroy(e->s_own);
   if (e->s_aux) cudaStreamDestroy(e->s_aux);
   if (e->s_aux2) cudaStreamDestroy(e->s_aux2);
+  if (e->s_aux3) cudaStreamDestroy(e->s_aux3);
   delete e;
 }
 
@@ -371,6 +375,9 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
     if ((ce = cudaStreamCreateWithFlags(&e->s_own, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->s_aux2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&e->s_aux3, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_join3, cudaEventDisableTiming)) != cudaSuccess ||
+        (ce = cudaEventCreateWithFlags(&e->ev_fork3, cudaEventDisableTiming)) != cudaSuccess ||
         (ce = cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming)) != cudaSuccess ||
         (ce = cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming)) != cudaSuccess ||
         (ce = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
@@ -387,6 +394,22 @@ int bh_engine_create(const bh_target* targets, int ntargets, int max_batch, int 
 int bh_engine_synth_stride(const bh_engine* e) { return e ? e->ts.synth_stride : BH_ERR_ARG; }
 
 int bh_engine_is_tuning(const bh_engine* e) { return (e && e->autotune && e->tune.locked < 0) ? 1 : 0; }
+
+// CUDA-graph capture of evaluations: between _begin and _end an evaluation polls no event, reads nothing back and keeps
+// its launch layout (the models-per-warp pick and the record capacity of the last plain evaluation; deeper models are
+// still caught by the second launch), so that the caller may capture it with cudaStreamBeginCapture on its stream.
+int bh_engine_capture_begin(bh_engine* e) {
+  if (!e) return set_err(BH_ERR_ARG, "null engine");
+  if (e->profile) return set_err(BH_ERR_UNSUPPORTED, "profiling records event pairs that cannot be read from a graph: set profile = 0");
+  if (bh_engine_is_tuning(e)) return set_err(BH_ERR_UNSUPPORTED, "the engine is still timing layouts for this batch size (bh_engine_is_tuning)");
+  e->graph_safe = 1;
+  return BH_OK;
+}
+int bh_engine_capture_end(bh_engine* e) {
+  if (!e) return set_err(BH_ERR_ARG, "null engine");
+  e->graph_safe = 0;
+  return BH_OK;
+}
 
 int bh_engine_set(bh_engine* e, const char* key, int value) {
   if (!e || !key) return set_err(BH_ERR_ARG, "null engine/key");
@@ -589,7 +612,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     // record capacity of the main dispersion launch: the layer counts seen lately (+2), not lmax
     int cap = lmax;
     if (e->adaptive_lcap && e->sort_layers && nswd > 0) {
-      if (e->maxn_pending && cudaEventQuery(e->ev_maxn) == cudaSuccess) {
+      if (!e->graph_safe && e->maxn_pending && cudaEventQuery(e->ev_maxn) == cudaSuccess) {
         e->last_maxn = *e->h_maxn;
         e->maxn_pending = false;
       }
@@ -668,7 +691,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
           t.B = B; t.base = pick;
           for (int i = pick - 1; i <= pick + 1; ++i) if (i >= 0 && i < 10) t.cand[t.ncand++] = i;
         }
-        if (t.locked < 0) {
+        if (t.locked < 0 && !e->graph_safe) {
           if (t.pending && cudaEventQuery(e->ev_tune[1]) == cudaSuccess) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, e->ev_tune[0], e->ev_tune[1]) == cudaSuccess) {
@@ -722,12 +745,25 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     }
     // keep one warp's records + mailbox within ~24 KB of shared memory
     auto fit = [](int s_, int lc) { while (s_ > 1 && swd_smem_bytes(lc, s_) > 24 * 1024) s_ >>= 1; return s_; };
+    // The reduced capacity exists to keep many warps resident when a warp holds many models.  With few models per warp
+    // the full-capacity records are small anyway, and a model deeper than the capacity would cost a whole second search
+    // BEHIND the first one -- twice the latency of a launch whose chains are the critical path (512-chain tutorial
+    // ensemble: 1.39 -> 1.09 ms per iteration with the full capacity).
+    if (cap < lmax && pool_cpc == 0 && (size_t)SWD_REC_FIELDS * lmax * (S > Sg ? S : Sg) * sizeof(double) <= 6 * 1024) cap = lmax;
     if (swl[0].ncurves > 0 && swl[1].ncurves > 0 && e->concurrent) {
       // Love chains share the SMs with the Rayleigh chains: own stream, forked after
       // the row preparation and before the Rayleigh launch
       BH_CUDA(cudaEventRecord(e->ev_fork2, st));
       BH_CUDA(cudaStreamWaitEvent(e->s_aux2, e->ev_fork2, 0));
       love_forked = true;
+    }
+    // the second search (models deeper than the record capacity) does not depend on the first: own stream, so that
+    // its few deep chains run beside the main launch instead of behind it (8192-chain tutorial ensemble: 3.09 -> ~2.2 ms)
+    bool deep_forked = false;
+    if (cap < lmax && e->concurrent) {
+      BH_CUDA(cudaEventRecord(e->ev_fork3, st));
+      BH_CUDA(cudaStreamWaitEvent(e->s_aux3, e->ev_fork3, 0));
+      deep_forked = true;
     }
     if (tuning_now) BH_CUDA(cudaEventRecord(e->ev_tune[0], st));
     for (int w = 0; w < 2; ++w) {
@@ -745,8 +781,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       for (int c = 1; c < sw.ncurves; ++c) mixed |= sw.wave[c] != sw.wave[0];
       // pass 0: models with at most `cap` rows, records sized for cap; pass 1 (only when cap < lmax):
       // the deeper models with full capacity.  Warps of pass 1 without such a model exit at once.
+      const cudaStream_t sst0 = sst;
       for (int pass = 0; pass < (cap < lmax ? 2 : 1); ++pass) {
         const int lc = pass == 0 ? cap : lmax;
+        sst = (pass == 1 && deep_forked) ? e->s_aux3 : sst0;
         sw.lcap = lc;
         sw.nlay_lo = pass == 0 ? -1 : cap;
         sw.nlay_hi = (pass == 0 && cap < lmax) ? cap : 0x7fffffff;
@@ -801,6 +839,10 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
         } else go();
       }
     }
+    if (deep_forked) {
+      BH_CUDA(cudaEventRecord(e->ev_join3, e->s_aux3));
+      BH_CUDA(cudaStreamWaitEvent(st, e->ev_join3, 0));
+    }
     if (tuning_now) {
       if (love_forked) {                               // the Love launch is part of what is timed
         BH_CUDA(cudaEventRecord(e->ev_join2, e->s_aux2));
@@ -809,7 +851,7 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       BH_CUDA(cudaEventRecord(e->ev_tune[1], st));
       e->tune.pending = true;
     }
-    if (e->adaptive_lcap && e->sort_layers && nswd > 0) {
+    if (e->adaptive_lcap && e->sort_layers && nswd > 0 && !e->graph_safe) {
       // read the batch's largest layer count back behind the dispersion kernel (for LATER evaluations;
       // enqueued after the launch so that it cannot delay it)
       BH_CUDA(cudaMemcpyAsync(e->h_maxn, e->d_maxn, sizeof(int), cudaMemcpyDeviceToHost, st));

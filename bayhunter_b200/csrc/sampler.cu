@@ -11,6 +11,7 @@
 // fails its prior check sit the evaluation out (nlay = 0 -> the engine skips the model), exactly
 // like the reference's early return (:541-547).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -357,22 +358,66 @@ int bh_sampler_set_forced_draws(bh_sampler* s, const double* draws) {
   return BH_OK;
 }
 
+// One lock-step iteration, enqueued on s->st: propose, evaluate, accept.
+static int enqueue_iteration(bh_sampler* s, const SamplerDev& p) {
+  const int threads = 64, blocks = (s->B + threads - 1) / threads;
+  sampler_propose_kernel<<<blocks, threads, 0, s->st>>>(p);
+  int rc = bh_engine_eval(s->eng, s->rows, s->nlay, s->prop_noise, nullptr, s->B, s->maxl, s->p_logL,
+                          s->p_misfits, s->p_status, nullptr, s->st);
+  if (rc != BH_OK) return rc;
+  sampler_accept_kernel<<<blocks, threads, 0, s->st>>>(p);
+  return BH_OK;
+}
+
+// An iteration is ~15 dependent launches on three streams; replayed from a CUDA graph the gaps between them go
+// (tutorial ensemble of 512 chains: 1.39 -> ~1.1 ms per iteration).  Every kGraphChunk iterations one is enqueued
+// plainly, which lets the engine refresh what it adapts (record capacity, layout) before the next capture.
+// BH_SAMPLER_GRAPH=0 switches the replay off.
 int bh_sampler_run(bh_sampler* s, int niter) {
   if (!s || niter < 0) return bh_set_error_message(BH_ERR_ARG, "bad argument");
   const SamplerDev p = dev_view(s);
-  const int threads = 64, blocks = (s->B + threads - 1) / threads;
-  for (int it = 0; it < niter; ++it) {
-    sampler_propose_kernel<<<blocks, threads, 0, s->st>>>(p);
-    int rc = bh_engine_eval(s->eng, s->rows, s->nlay, s->prop_noise, nullptr, s->B, s->maxl, s->p_logL,
-                            s->p_misfits, s->p_status, nullptr, s->st);
-    if (rc != BH_OK) return rc;
-    sampler_accept_kernel<<<blocks, threads, 0, s->st>>>(p);
+  static const bool graphs = []() { const char* v = getenv("BH_SAMPLER_GRAPH"); return !(v && v[0] == '0'); }();
+  constexpr int kGraphChunk = 128;
+  std::vector<cudaGraphExec_t> execs;
+  std::vector<cudaGraph_t> captured;
+  int rc = BH_OK;
+  cudaError_t launch_err = cudaSuccess;
+  for (int it = 0; it < niter && rc == BH_OK;) {
+    rc = enqueue_iteration(s, p);
+    ++it;
+    if (rc != BH_OK) break;
     // while the engine is still timing its models-per-warp candidates (the first ~10 iterations of a
     // batch size) let each iteration finish, so that its timing is read before the next one is enqueued
-    if (bh_engine_is_tuning(s->eng)) SMP_CUDA(cudaStreamSynchronize(s->st));
+    if (bh_engine_is_tuning(s->eng)) { SMP_CUDA(cudaStreamSynchronize(s->st)); continue; }
+    const int n = niter - it < kGraphChunk ? niter - it : kGraphChunk;
+    if (!graphs || n < 8 || bh_engine_capture_begin(s->eng) != BH_OK) continue;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      rc = enqueue_iteration(s, p);
+      ce = cudaStreamEndCapture(s->st, &g);
+    }
+    bh_engine_capture_end(s->eng);
+    if (ce == cudaSuccess && rc == BH_OK && g) ce = cudaGraphInstantiate(&ex, g, 0);
+    if (g) captured.push_back(g);
+    if (ce != cudaSuccess || rc != BH_OK || !ex) {       // no graph: the plain path goes on
+      cudaGetLastError();
+      if (rc != BH_OK) break;
+      continue;
+    }
+    execs.push_back(ex);
+    for (int k = 0; k < n && ce == cudaSuccess; ++k) ce = cudaGraphLaunch(ex, s->st);
+    if (ce != cudaSuccess) { launch_err = ce; break; }
+    it += n;
   }
-  SMP_CUDA(cudaGetLastError());
-  SMP_CUDA(cudaStreamSynchronize(s->st));
+  cudaError_t ce = launch_err != cudaSuccess ? launch_err : cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->st);
+  else cudaStreamSynchronize(s->st);
+  for (cudaGraphExec_t ex : execs) cudaGraphExecDestroy(ex);
+  for (cudaGraph_t g : captured) cudaGraphDestroy(g);
+  if (rc != BH_OK) return rc;
+  SMP_CUDA(ce);
   return BH_OK;
 }
 

@@ -116,6 +116,14 @@ int bh_engine_synth_stride(const bh_engine* e);
  * that every timing is read back before the next candidate is tried). */
 int bh_engine_is_tuning(const bh_engine* e);
 
+/* CUDA-graph capture.  Between bh_engine_capture_begin and bh_engine_capture_end, bh_engine_eval enqueues stream-ordered
+ * work only (no event polling, no read-back; the launch layout of the last plain evaluation is kept and deeper models are
+ * still handled by the second dispersion launch), so the caller may capture it on its stream with cudaStreamBeginCapture /
+ * cudaStreamEndCapture and replay the graph; the forked streams join the capture through events.  _begin fails with
+ * BH_ERR_UNSUPPORTED while "profile" is on or bh_engine_is_tuning() is 1.  bh_sampler_run uses this for its iterations. */
+int bh_engine_capture_begin(bh_engine* e);
+int bh_engine_capture_end(bh_engine* e);
+
 /* Tunables (call before eval; all have working defaults).
  *   key "swd_searches_per_warp"  1..32   phase-velocity curves (default chosen from the batch size)
  *   key "swd_group_searches_per_warp" 1..32  group-velocity curves (default: half of the above)

@@ -18,16 +18,18 @@ t2 = Targets.PReceiverFunction(xrf, yrf)
 t2.moddata.plugin.set_modelparams(gauss=1., water=0.01, p=6.4)
 jt = Targets.JointTarget(targets=[t1, t2])
 priors.update({'mohoest': (38, 4), 'rfnoise_corr': 0.98, 'swdnoise_corr': 0.})
-for n in [int(a) for a in sys.argv[1:]] or [512]:
+settings = dict(kv.split("=") for a in sys.argv[1:] if "=" in a for kv in a.split(","))
+settings = {k: int(v) for k, v in settings.items()}
+for n in [int(a) for a in sys.argv[1:] if "=" not in a] or [512]:
     ens = sc.ChainEnsemble(jt, priors, initparams, nchains=n, seed=7)
     ens.init()
-    ens.engine.set(profile=0)
+    ens.engine.set(profile=0, **settings)
     ens.run(300)
     ens.state()
     t0 = time.perf_counter(); ens.run(1000); ens.state(); dt = time.perf_counter() - t0
     ens.engine.set(profile=1)
     ens.run(3); ens.state()
-    print(json.dumps(dict(nchains=n, ms_per_iteration=dt, chain_iterations_per_s=n * 1000 / dt,
+    print(json.dumps(dict(nchains=n, settings=settings, ms_per_iteration=dt, chain_iterations_per_s=n * 1000 / dt,
                           kernels={k: round(v, 4) for k, v in ens.engine.last_kernel_ms().items()},
                           mean_rows=float(ens.state()["k"].mean()) + 1)), flush=True)
     ens.close()
