@@ -335,6 +335,22 @@ def test_ensembles_own_their_engines_and_overflow_is_per_chain(oracle):
     a.close(); b.close()
 
 
+def test_sampler_graph_replay_changes_nothing():
+    """bh_sampler_run replays its iterations from CUDA graphs (captured between bh_engine_capture_begin / _end):
+    the final state of a transdimensional run is bit-identical to the plainly enqueued one."""
+    import os, subprocess, sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sampler_graph_worker.py")
+    out = {}
+    for g in ("0", "1"):
+        env = dict(os.environ, BH_SAMPLER_GRAPH=g)
+        r = subprocess.run([sys.executable, worker], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1].split()
+        out[g] = line[1:]
+    assert out["0"] == out["1"], out
+    assert int(out["1"][1]) == 300 and int(out["1"][2]) > 1000
+
+
 @pytest.mark.parametrize("law,corr", [("exp", 0.85), ("gauss", 0.9), ("exp", 0.0)])
 def test_device_noise_has_the_reference_distribution(law, corr):
     """bh_correlated_noise against the numpy recipe of SynthObs (src/SynthObs.py:136-155): same covariance
