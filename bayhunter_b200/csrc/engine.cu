@@ -651,11 +651,13 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
         if (target < t2) target = t2;
       }
       // small batches: the chains are the critical path and the machine is far from full -- one warp per SM
-      // sub-partition (as long as a warp keeps two chains) before chains are packed 14 to a warp
-      // (profiles/r01_variants.txt: joint5 B = 256 / 512 / 1024: 1.81 -> 1.49 / 1.58 / 1.72 ms)
+      // sub-partition, down to one chain per warp (its idle lanes walk 16 steps a round and carry the refinement
+      // guesses), before chains are packed
+      // (profiles/r01_variants.txt: joint5 B = 256 / 512 / 1024: 1.81 -> 1.49 / 1.58 / 1.72 ms; r02 section 17:
+      //  one chain instead of two per warp, 512-chain tutorial ensemble 1.11 -> 1.04 ms per iteration)
       if (e->nsm > 0) {
         long long fill = 4LL * e->nsm;
-        if (fill > chains / 2) fill = chains / 2;
+        if (fill > chains) fill = chains;
         if (target < fill) target = fill;
       }
       static const int cand[][2] = {{32, 16}, {16, 16}, {16, 8}, {8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {2, 1}, {1, 1}};
