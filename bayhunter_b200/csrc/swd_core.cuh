@@ -955,18 +955,26 @@ BH_HD int search_nwant(const Search& s, int nmax) {
 // i-th pending candidate (i = 0 is the one the reference evaluates next).
 // The published (stage, c, idir, clow) tuple is all a worker lane needs.
 // A refining chain (stage > ST_BR_STEP) publishes c = c3, clow = c1 and c2: candidate 0 is c3, candidates 1 and 2 are
-// the two midpoints the NEXT step asks for if it bisects, candidates 3..6 the four midpoints the step after that
-// can ask for if both bisect (refine_guess; search_consume uses a value only if the step asks for exactly that velocity).
+// the two midpoints the NEXT step asks for if it bisects, 3..6 the four midpoints the step after that can ask for if
+// both bisect, 7..14 those of a third step: a binary tree in heap order (node i has the children 2i + 1, 2i + 2; the
+// left child halves the bracket on the c1 side).  search_consume uses a value only if the step asks for exactly that
+// velocity.
 BH_HD double refine_guess(double c1, double c2, double c3, int i) {
-  const double g1 = 0.5 * (c1 + c3), g2 = 0.5 * (c3 + c2);
-  switch (i) {
-    case 1: return g1;
-    case 2: return g2;
-    case 3: return 0.5 * (c1 + g1);
-    case 4: return 0.5 * (g1 + c3);
-    case 5: return 0.5 * (c3 + g2);
-    default: return 0.5 * (g2 + c2);
+  int dirs = 0, depth = 0;
+  for (int j = i; j > 0; j = (j - 1) >> 1) { dirs = (dirs << 1) | ((j & 1) ? 0 : 1); ++depth; }   // root step in bit 0
+  double lo = c1, hi = c2, pt = c3;
+  for (int d = 0; d < depth; ++d) {
+    if (dirs & 1) lo = pt; else hi = pt;
+    dirs >>= 1;
+    pt = 0.5 * (lo + hi);
   }
+  return pt;
+}
+// Guess lanes per refining chain: the deepest tree that fits `room` lanes for `nrf` refining chains.
+constexpr int kRefineGuesses = 2, kRefineGuesses2 = 6, kRefineGuesses3 = 14;
+BH_HD int refine_guess_lanes(int nrf, int room) {
+  if (nrf <= 0) return 0;
+  return kRefineGuesses3 * nrf <= room ? kRefineGuesses3 : (kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0));
 }
 BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i, double c2r = 0.0) {
   if (stage > ST_BR_STEP) return i == 0 ? c : refine_guess(clow, c2r, c, i);
@@ -995,9 +1003,8 @@ BH_HD double search_pending_c(const Search& s) {
 // (extra + 0.5) / nbr stays >= 1/64 away from every integer for 0 <= extra <= 32, 1 <= nbr <= 32, far beyond
 // the error of the approximate fp32 quotient.
 // When lanes are left over even after every walking chain has four (small batches, deep models), each refining chain gets
-// kRefineGuesses more for the two midpoints its next step may ask for, or kRefineGuesses2 for those of its next two
-// steps (search_consume).
-constexpr int kRefineGuesses = 2, kRefineGuesses2 = 6;
+// 2 more for the two midpoints its next step may ask for, or 6 / 14 for those of its next two / three steps
+// (refine_guess_lanes, search_consume).
 #ifndef BH_GUESS_WALK_EXTRA
 #define BH_GUESS_WALK_EXTRA 3
 #endif
@@ -1010,8 +1017,7 @@ BH_HD LaneDeal deal_lanes(unsigned active, unsigned bracket, int lane, int max_s
 #endif
   const int nact = BH_POPC(active), nbr = BH_POPC(bracket);
   const int nrf = nact - nbr;
-  const int room = 32 - nact - BH_GUESS_WALK_EXTRA * nbr;
-  const int g = nrf == 0 ? 0 : (kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0));
+  const int g = refine_guess_lanes(nrf, 32 - nact - BH_GUESS_WALK_EXTRA * nbr);
   const int extra = 32 - nact - g * nrf;
 #if defined(__CUDA_ARCH__)
   const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
@@ -1187,27 +1193,20 @@ BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& c
     case ST_RF_TOP:
     case ST_RF_POST: {
       // values 1 and 2 (if dealt) belong to the midpoints of the two half brackets this step can leave behind
-      const double o1 = s.c1, o2 = s.c2, o3 = s.c3;
+      double lo = s.c1, hi = s.c2, pt = s.c3;
       s.del3 = del[0];
-      int used = 1;
+      int used = 1, node = 0;
       bool done = nevill_resume(s, s.stage == ST_RF_TOP);
-      if (guesses && !done && n > kRefineGuesses) {
-        // the step bisected into one of the two half brackets: its value is here already
-        const int i1 = s.c3 == refine_guess(o1, o2, o3, 1) ? 1 : (s.c3 == refine_guess(o1, o2, o3, 2) ? 2 : 0);
-        if (i1) {
-          s.del3 = del[i1];
-          used = 2;
-          done = nevill_resume(s, s.stage == ST_RF_TOP);
-          if (!done && n > kRefineGuesses2) {
-            const int ia = 2 * i1 + 1, ib = ia + 1;              // the two halves of that half
-            const int i2 = s.c3 == refine_guess(o1, o2, o3, ia) ? ia : (s.c3 == refine_guess(o1, o2, o3, ib) ? ib : 0);
-            if (i2) {
-              s.del3 = del[i2];
-              used = 3;
-              done = nevill_resume(s, s.stage == ST_RF_TOP);
-            }
-          }
-        }
+      // the step bisected into one of the two half brackets: its value is here already, and so on down the tree
+      while (guesses && !done && 2 * node + 2 < n) {
+        const double gl = 0.5 * (lo + pt), gr = 0.5 * (pt + hi);
+        if (s.c3 == gl) { hi = pt; node = 2 * node + 1; }
+        else if (s.c3 == gr) { lo = pt; node = 2 * node + 2; }
+        else break;
+        pt = s.c3;
+        s.del3 = del[node];
+        used += 1;
+        done = nevill_resume(s, s.stage == ST_RF_TOP);
       }
       if (done) search_root_end(s, ctx, s.c3, !(s.c3 > s.betmx));        // :475-476
       return used;

@@ -172,11 +172,7 @@ swd_pool_kernel(SwdLaunch p, int M) {
     rank += __popc(b_w & below);
     // dealing rule of swd_core.cuh (deal_lanes), over the CTA's lanes
     const int nrf = nact - nbr;
-    int g = 0;
-    if (kGuess && nrf > 0) {
-      const int room = kPoolLanes - nact - BH_GUESS_WALK_EXTRA * nbr;
-      g = kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0);
-    }
+    const int g = kGuess ? refine_guess_lanes(nrf, kPoolLanes - nact - BH_GUESS_WALK_EXTRA * nbr) : 0;
     const int extra = kPoolLanes - nact - g * nrf;
     const int quo = nbr ? __float2int_rz(__fdividef((float)extra + 0.5f, (float)nbr)) : 0;
     const int rem = extra - quo * nbr;
