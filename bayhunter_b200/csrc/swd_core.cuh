@@ -956,7 +956,7 @@ BH_HD int search_nwant(const Search& s, int nmax) {
 // The published (stage, c, idir, clow) tuple is all a worker lane needs.
 // A refining chain (stage > ST_BR_STEP) publishes c = c3, clow = c1 and c2: candidate 0 is c3, candidates 1 and 2 are
 // the two midpoints the NEXT step asks for if it bisects, 3..6 the four midpoints the step after that can ask for if
-// both bisect, 7..14 those of a third step: a binary tree in heap order (node i has the children 2i + 1, 2i + 2; the
+// both bisect, 7..14 and 15..30 those of a third and fourth step: a binary tree in heap order (node i has the children 2i + 1, 2i + 2; the
 // left child halves the bracket on the c1 side).  search_consume uses a value only if the step asks for exactly that
 // velocity.
 BH_HD double refine_guess(double c1, double c2, double c3, int i) {
@@ -971,9 +971,10 @@ BH_HD double refine_guess(double c1, double c2, double c3, int i) {
   return pt;
 }
 // Guess lanes per refining chain: the deepest tree that fits `room` lanes for `nrf` refining chains.
-constexpr int kRefineGuesses = 2, kRefineGuesses2 = 6, kRefineGuesses3 = 14;
+constexpr int kRefineGuesses = 2, kRefineGuesses2 = 6, kRefineGuesses3 = 14, kRefineGuesses4 = 30;
 BH_HD int refine_guess_lanes(int nrf, int room) {
   if (nrf <= 0) return 0;
+  if (kRefineGuesses4 * nrf <= room) return kRefineGuesses4;      // a chain alone in its warp
   return kRefineGuesses3 * nrf <= room ? kRefineGuesses3 : (kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0));
 }
 BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i, double c2r = 0.0) {
@@ -1003,7 +1004,7 @@ BH_HD double search_pending_c(const Search& s) {
 // (extra + 0.5) / nbr stays >= 1/64 away from every integer for 0 <= extra <= 32, 1 <= nbr <= 32, far beyond
 // the error of the approximate fp32 quotient.
 // When lanes are left over even after every walking chain has four (small batches, deep models), each refining chain gets
-// 2 more for the two midpoints its next step may ask for, or 6 / 14 for those of its next two / three steps
+// 2 more for the two midpoints its next step may ask for, or 6 / 14 / 30 for those of its next two / three / four steps
 // (refine_guess_lanes, search_consume).
 #ifndef BH_GUESS_WALK_EXTRA
 #define BH_GUESS_WALK_EXTRA 3

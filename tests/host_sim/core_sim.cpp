@@ -80,8 +80,8 @@ int swd_sim_curve(const float* rows4, int nlayer, int wave, int igr, int kmax, c
       // a refining chain with lanes to spare also gets the two midpoints its next step may ask for (deal_lanes)
       const bool refining = s.stage == ST_RF_TOP || s.stage == ST_RF_POST;
       if (refining && spec_mode != 0 && (spec_mode > 0 ? spec_mode >= 3 : (lcg(rng) & 1)))
-        n[r] = 1 + (spec_mode > 0 ? (spec_mode >= 15 ? kRefineGuesses3 : spec_mode >= 7 ? kRefineGuesses2 : kRefineGuesses)
-                                  : (lcg(rng) % 3 == 0 ? kRefineGuesses3 : (lcg(rng) & 1) ? kRefineGuesses2 : kRefineGuesses));
+        n[r] = 1 + (spec_mode > 0 ? (spec_mode >= 31 ? kRefineGuesses4 : spec_mode >= 15 ? kRefineGuesses3 : spec_mode >= 7 ? kRefineGuesses2 : kRefineGuesses)
+                                  : (lcg(rng) % 4 == 0 ? kRefineGuesses4 : lcg(rng) % 3 == 0 ? kRefineGuesses3 : (lcg(rng) & 1) ? kRefineGuesses2 : kRefineGuesses));
       any += n[r];
       double cpub = search_pending_c(s);
       for (int i = 0; i < n[r]; ++i) {

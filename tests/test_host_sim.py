@@ -129,7 +129,7 @@ def test_device_formulation_of_secular_functions(oracle, host_sim):
 
 def test_lane_dealing_closed_form(host_sim):
     """deal_lanes (popcounts of the two ballots) against the sequential definition: one lane per refining
-    chain (3, 7 or 15 when lanes are left over even with four per walking chain), the spare lanes dealt evenly to the walking chains in lane order (the first `extra % nbr` of them
+    chain (3, 7, 15 or 31 when lanes are left over even with four per walking chain), the spare lanes dealt evenly to the walking chains in lane order (the first `extra % nbr` of them
     one more), at most max_spec per chain; runs laid out in lane order without gaps."""
     rng = np.random.default_rng(5)
     I32 = ctypes.c_int * 32
@@ -148,7 +148,7 @@ def test_lane_dealing_closed_form(host_sim):
         nrf = nact - nbr
         # lanes left over even with four per walking chain: two guess lanes per refining chain
         room = 32 - nact - 3 * nbr
-        g = 0 if nrf == 0 else (14 if 14 * nrf <= room else (6 if 6 * nrf <= room else (2 if 2 * nrf <= room else 0)))
+        g = 0 if nrf == 0 else next((t for t in (30, 14, 6, 2) if t * nrf <= room), 0)
         extra = 32 - nact - g * nrf
         cnt_ref = []
         for l in range(32):
