@@ -649,6 +649,12 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
         const long long cap2 = e->nsm > 0 ? (lmax > 12 ? 14LL : 11LL) * e->nsm + e->nsm / 8 : 1650;
         if (t2 > cap2) t2 = cap2;
         if (target < t2) target = t2;
+        // and with the guess trees up to 30 lanes deep, 1.5 chains per warp up to 7.5 warps per SM
+        // (section 17: joint5 B = 256 1.04 -> 0.89 ms, swd2 B = 1024 0.95 -> 0.85)
+        long long t3 = chains * 2 / 3;
+        const long long cap3 = e->nsm > 0 ? 7LL * e->nsm + e->nsm / 2 : 1100;
+        if (t3 > cap3) t3 = cap3;
+        if (target < t3) target = t3;
       }
       // small batches: the chains are the critical path and the machine is far from full -- one warp per SM
       // sub-partition, down to one chain per warp (its idle lanes walk 16 steps a round and carry the refinement
