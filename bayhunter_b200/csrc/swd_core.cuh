@@ -977,7 +977,9 @@ BH_HD int refine_guess_lanes(int nrf, int room) {
   if (kRefineGuesses4 * nrf <= room) return kRefineGuesses4;      // a chain alone in its warp
   return kRefineGuesses3 * nrf <= room ? kRefineGuesses3 : (kRefineGuesses2 * nrf <= room ? kRefineGuesses2 : (kRefineGuesses * nrf <= room ? kRefineGuesses : 0));
 }
-BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i, double c2r = 0.0) {
+// fast_up: the shortcut for upward walks (same operations; measured faster in swd_pool_kernel, slower in swd_kernel)
+BH_HD double candidate_from(int stage, double c, int idir, double clow, double dc, int i, double c2r = 0.0,
+                            const bool fast_up = false) {
   if (stage > ST_BR_STEP) return i == 0 ? c : refine_guess(clow, c2r, c, i);
   if (stage == ST_BR_FIRST) {            // c1 itself, then the upward walk from it
     if (i == 0) return c;
@@ -985,6 +987,12 @@ BH_HD double candidate_from(int stage, double c, int idir, double clow, double d
     i -= 1;
   }
   double c1 = c, c2 = c;
+  if (fast_up && idir > 0) {
+    // walking up, only the first step can be lifted to the lower end of the window; from then on c2 = c1 + dc
+    c2 = bracket_next(c1, idir, clow, dc);
+    for (int j = 1; j <= i; ++j) c2 += dc;
+    return c2;
+  }
   for (int j = 0; j <= i; ++j) {
     c2 = bracket_next(c1, idir, clow, dc);
     c1 = c2;
@@ -1157,7 +1165,8 @@ BH_HD bool nevill_resume(Search& s, bool at_top) {
 // this round (n = 1 unless stage == ST_BR_STEP).  Returns how many of the n
 // values were consumed (the rest was speculation past a sign change or past
 // the search window).
-BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& ctx, const bool guesses = true) {
+BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& ctx, const bool guesses = true,
+                         const bool fast_up = false) {
   int first = 0;
   switch (s.stage) {
     case ST_BR_FIRST: {
@@ -1173,6 +1182,34 @@ BH_HD int search_consume(Search& s, const double* del, int n, const SearchCtx& c
     }
     // fall through
     case ST_BR_STEP: {
+      if (fast_up && s.idir > 0 && first < n) {
+        // the upward walk (94 % of the searches): the same steps with the state in registers and without the
+        // per-step test against the lower end of the window, which only the first step can fail
+        const double lim = s.betmx + s.dc;
+        double c1 = s.c1, d1 = s.del1;
+        double c2 = bracket_next(c1, s.idir, s.clow, s.dc), d2 = 0.0;
+        int i = first;
+        for (;;) {
+          d2 = del[i];
+          if (sign_differs(d1, d2)) {                                    // :462 -> nevill
+            s.c1 = c1; s.del1 = d1; s.c2 = c2; s.del2 = d2;
+            nevill_request_half(s, ST_RF_TOP);                           // :583
+            s.nev = 1;
+            s.nctrl = 1;
+            return i + 1;
+          }
+          c1 = c2; d1 = d2;
+          if (c1 < s.cc || c1 >= lim) {                                  // :468-469 (cm = cc)
+            s.c1 = c1; s.del1 = d1; s.c2 = c2; s.del2 = d2;
+            search_root_end(s, ctx, 0.0, false);
+            return i + 1;
+          }
+          if (++i >= n) break;
+          c2 = c1 + s.dc;
+        }
+        s.c1 = c1; s.del1 = d1; s.c2 = c2; s.del2 = d2;
+        return n;
+      }
       for (int i = first; i < n; ++i) {
         s.c2 = bracket_next(s.c1, s.idir, s.clow, s.dc);
         s.del2 = del[i];

@@ -208,7 +208,7 @@ swd_pool_kernel(SwdLaunch p, int M) {
       const int i = t - start;
       const int own = ws->owner_at[start];
       const double omega = ws->omega[own];
-      const double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i, kGuess ? ws->c2[own] : 0.0);
+      const double c = candidate_from(ws->stage[own], ws->c[own], ws->idir[own], ws->clow[own], dc, i, kGuess ? ws->c2[own] : 0.0, true);
       ws->del[t] = secular_rec(wave, rec + ws->col[own], fs, M, ws->nlay[own], fm::div(omega, c), omega);
       evaluated += 1;
     }
@@ -219,7 +219,7 @@ swd_pool_kernel(SwdLaunch p, int M) {
     // ---- phase C: owners consume their values in reference order ----
     if (t < kPoolWarps) ws->startbits[t] = 0u;
     if (t == 0) ws->any_wait = 0;
-    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx, kGuess);
+    if (cnt > 0) consumed += search_consume(s, &ws->del[excl], cnt, ctx, kGuess, true);
     BH_TICK(6)
     __syncthreads();
     BH_TICK(7)
