@@ -523,20 +523,19 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
     gen.mode[c] = d.mode; gen.flsph[c] = d.flsph;
     gen.periods[c] = d.periods; gen.curve_off[c] = e->curve_off[t];
   }
-  // The pool kernel (swd_pool.cu) pays when its CTAs fill the device four to an SM: -5 % at 8 k (model, wave type) pairs
-  // (14 models per CTA, lanes to spare for refinement guesses), -5 % at 16 k (28 models per CTA), -9 % at 32 k; slower
-  // below ~6 k pairs and with one wave type only (profiles/r02_swd_restructure.txt sections 12, 15).
+  // The pool kernel (swd_pool.cu) against swd_kernel, joint5 unless noted (profiles/r02_swd_restructure.txt sections 12,
+  // 15, 16, 19): B = 2560 2.18 -> 1.94 ms, 4096 2.55 -> 2.36, 8192 3.64 -> 3.36, 16384 7.14 -> 6.47; slower at B <= 2048.
+  // With one wave type: deep models (transd3) from ~1800 models, 2048: 5.12 -> 4.54, 4096: 6.34 -> 5.58, 8192: 9.49 -> 7.61;
+  // shallow models (swd2) only between ~4 k and ~8 k models at 14 per CTA (4096: 1.47 -> 1.42, 8192: 2.08 -> 1.97;
+  // 2048 and 16384: swd_kernel is faster).
   int pool_cpc = 0;      // chains per CTA of the pool kernel; 0: swd_kernel
   if (e->pool != 0 && nswd > 0) {
     const int nl = (swl[0].ncurves > 0) + (swl[1].ncurves > 0);
-    // rule: Rayleigh and Love CTAs side by side (one wave type alone: equal at best for shallow models -- swd2 B = 4096
-    // 1.48 / 1.48 ms, B = 16384 3.02 / 3.09), or deep models, whose long evaluations make the shared lanes pay with one
-    // wave type too (transd3 B = 4096 6.34 -> 5.80 ms at 8 models per CTA, B = 8192 9.49 -> 7.70 at 14)
     const bool deep = lmax > 12;
-    bool fits = (e->pool == 1 ? (nl == 1 || e->concurrent) : ((nl == 2 && e->concurrent) || (nl == 1 && deep))) && !e->lockstep;
+    bool fits = (nl == 1 || e->concurrent) && !e->lockstep;
     for (int w = 0; w < 2; ++w) fits = fits && (swl[w].ncurves == 0 || swd_pool_fits(swl[w]));
-    // counted in chains (3 per model with a group and a phase curve): 42..96 chains per CTA (14..32 such models), from 24
-    // for deep models with one wave type; as many chains per CTA as fill four CTAs per SM
+    // counted in chains (3 per model with a group and a phase curve): as many per CTA as fill four CTAs per SM, within
+    // 26..96 with both wave types, 24..96 for deep models with one, 42 for shallow models with one
     long long chains = 0;
     int cpm_max = 1;
     for (int w = 0; w < 2; ++w) {
@@ -546,12 +545,17 @@ int bh_engine_eval(bh_engine* e, const double* model, const int* nlay, const dou
       if (cpm > cpm_max) cpm_max = cpm;
     }
     const long long slots = 4LL * e->nsm;
-    const int clo = (nl == 1 && deep) ? 24 : 42;
+    const int clo = nl == 2 ? 26 : (deep ? 24 : 42);
     int cpc = slots > 0 ? (int)((chains + slots - 1) / slots) : 84;
     cpc = cpc < clo ? clo : (cpc > 96 ? 96 : cpc);
-    if (fits && (e->pool == 1 || (e->nsm > 0 && e->searches_per_warp == 0 && chains * 100 >= slots * clo * (deep ? 85 : 90) &&
-                                  swd_pool_smem_bytes(lmax, (cpc + cpm_max - 1) / cpm_max) * 4 <= (size_t)220 * 1024)))
-      pool_cpc = cpc;
+    bool pays = false;
+    if (e->nsm > 0 && e->searches_per_warp == 0) {
+      if (nl == 2) pays = chains * 100 >= slots * clo * 95;
+      else if (deep) pays = chains * 100 >= slots * clo * 38;           // ~5.4 k chains on 148 SMs
+      else { pays = chains * 100 >= slots * 42 * 46 && chains <= slots * 44; cpc = 42; }
+      pays = pays && swd_pool_smem_bytes(lmax, (cpc + cpm_max - 1) / cpm_max) * 4 <= (size_t)220 * 1024;
+    }
+    if (fits && (e->pool == 1 || pays)) pool_cpc = cpc;
   }
   if (!e->split_waves && pool_cpc == 0 && swl[0].ncurves > 0 && swl[1].ncurves > 0) {
     // one mixed launch: append the Love curves to the Rayleigh launch

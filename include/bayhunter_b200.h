@@ -146,9 +146,9 @@ int bh_engine_capture_end(bh_engine* e);
  *   key "swd_max_spec"           1..32   speculative bracket candidates per search
  *   key "swd_pool"               -1/0/1  dispersion by swd_pool_kernel (a CTA's 128 lanes dealt over all chains of M
  *                                        models of one wave type, Rayleigh and Love launches side by side): by rule
- *                                        (default: both wave types present, >= ~3.7 k models per GPU), never, always
+ *                                        (default: from ~2.5 k models with both wave types, ~1.8 k deep models or 4-8 k shallow ones with one), never, always
  *                                        (results do not depend on it)
- *   key "swd_pool_models"        0..128  M of the above (0 = rule: models x wave types / (4 x SMs), 14..32)
+ *   key "swd_pool_models"        0..128  M of the above (0 = rule: as many chains per CTA as fill four CTAs per SM)
  *   key "swd_lockstep"           0/1     dispersion by swd_lockstep_kernel (every lane owns a chain; a measured
  *                                        negative result at these batch sizes, default 0)
  *   key "rf_prune_exp10"         0..300  receiver function: spectral bins whose Gauss-filter weight
